@@ -1,0 +1,221 @@
+/*
+ * amx.h -- C-ABI of automix-b200: the flat, torch-free doorway to the sm_100a
+ * kernels that replace LibAutoMix's sampling hot path.
+ *
+ * Plain C: pointers, sizes, opaque handles.  No CUDA or torch types appear in
+ * any signature (streams travel as void*).  The drop-in LibAutoMix API
+ * (include/automix.h: initAMSampler, estimate_conditional_probs, burn_samples,
+ * rjmcmc_samples, freeAMSampler) is implemented in C on top of exactly these
+ * calls (automix_b200/csrc/automix_host.c); a binding from another language
+ * binds these.
+ *
+ * Each block names the reference interface it replaces; citations are to
+ * /root/reference/src/libautomix/automix.c unless another file is given.
+ *
+ * Conventions
+ *   - all functions return 0 on success, a negative AMX_E* code on failure;
+ *     amx_last_error() gives the message (the reference has void returns and no
+ *     error channel: automix.h:86-100).
+ *   - "flat" mixture arguments follow include/amx_layout.h.
+ *   - *_dev entry points take device pointers and enqueue on the library stream
+ *     (amx_set_stream); the others take host pointers and include the copies.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with AMX_ENODEV.
+ */
+#ifndef AMX_H
+#define AMX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "amx_layout.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMX_OK 0
+#define AMX_EINVAL (-1)
+#define AMX_ENODEV (-2)
+#define AMX_ECUDA (-3)
+#define AMX_ENOMEM (-4)
+#define AMX_ETAPE (-5)   /* injected uniform tape exhausted */
+#define AMX_ENUMERIC (-6) /* non-positive-definite scatter, NaN log-posterior */
+
+/* ---- runtime ------------------------------------------------------------ */
+const char *amx_last_error(void);
+const char *amx_version(void);
+int amx_device_count(void);
+int amx_set_device(int ordinal);
+/* Library work is enqueued on this stream (a cudaStream_t passed as void*;
+ * NULL = the legacy default stream). */
+int amx_set_stream(void *cuda_stream);
+int amx_synchronize(void);
+/* Kernels launched by this library since the counter was last reset. */
+unsigned long long amx_launch_count(int reset);
+/* Dependent-free DFMA micro-benchmark: measured fp64 FLOP/s of this GPU
+ * (the roofline denominator for the fp64-bound kernels). */
+int amx_measure_fp64_peak(double *flops_per_s);
+
+/* ---- K4: mixture / MVN-Cholesky log-density ----------------------------- */
+/* Replaces lnormprob (:1727-1750) + det (:1752-1761), batched.
+ *   x        n x d row-major
+ *   comp_out n x L row-major component log-densities (may be NULL)
+ *   mix_out  n   log sum_l wt_l N(x; mean_l, tri_l tri_l^T)      (may be NULL)
+ */
+int amx_mix_logpdf(int d, int L, const double *wt, const double *mean,
+                   const double *tri, long n, const double *x, double *comp_out,
+                   double *mix_out);
+int amx_mix_logpdf_dev(int d, int L, const double *wt, const double *mean,
+                       const double *tri, long n, const double *x_dev,
+                       double *comp_out_dev, double *mix_out_dev);
+
+/* ---- log-posterior plug-ins --------------------------------------------- */
+/* The reference contract is `double f(int model_k, double *x)` (automix.h:46).
+ * Beside it: built-in __device__ families (full speed) and a batched host
+ * callback. */
+typedef struct amx_target amx_target;
+typedef double (*amx_scalar_fn)(int model_k, double *x);
+typedef void (*amx_batched_fn)(long n, const int *model_k, const double *x,
+                               long ldx, double *lp_out, void *user);
+
+#define AMX_GM_PLAIN 0 /* log(modw * sum_g c_g exp(-q_g/2)), as usertoy1.c:72-100 */
+#define AMX_GM_LSE 1   /* same value through log-sum-exp (no underflow) */
+
+/* Gaussian-mixture target: model k is modw[k] * sum_g wt N(mean, tri tri^T). */
+amx_target *amx_target_gaussmix(int nmodels, const int *dims, const int *ncomp,
+                                const double *modw, const double *wt,
+                                const double *mean, const double *tri,
+                                int flags);
+/* Separable quadratic: -sum_i (x_i-c_i)^2/(2 s_i^2) inside (lo_i,hi_i), else
+ * -DBL_MAX (tests/test_automix.c:242-265, README.md:66-73).  Arrays are the
+ * concatenation over models; lo/hi may be NULL (unbounded). */
+amx_target *amx_target_quad(int nmodels, const int *dims, const double *center,
+                            const double *scale, const double *lo,
+                            const double *hi);
+/* Coal-mining change-point posterior (src/user_examples/usercpt.c:46-134),
+ * models k=0..5, d=2k+3. */
+amx_target *amx_target_coalmine(void);
+amx_target *amx_target_host_scalar(int nmodels, const int *dims,
+                                   amx_scalar_fn f);
+amx_target *amx_target_host_batched(int nmodels, const int *dims,
+                                    amx_batched_fn f, void *user);
+void amx_target_destroy(amx_target *t);
+/* lp_out[i] = f(model_k[i], x[i*ldx ...]) evaluated by the plug-in on the GPU
+ * (device families) or through the callback (host families). */
+int amx_target_eval(const amx_target *t, long n, const int *model_k,
+                    const double *x, long ldx, double *lp_out);
+
+/* ---- proposal distribution (fitted mixtures + RWM scales) --------------- */
+/* The flat mirror of proposalDist (automix.h:134-153). */
+typedef struct amx_proposal amx_proposal;
+amx_proposal *amx_proposal_create(int nmodels, const int *dims,
+                                  const int *ncomp, const double *wt,
+                                  const double *mean, const double *tri,
+                                  const double *sig);
+void amx_proposal_destroy(amx_proposal *p);
+
+/* ---- K3: reversible-jump sweeps over a population of chains ------------- */
+/* Replaces initChain (:423-449), reversible_jump_move (:1035-1288) and the
+ * sweep loops of burn_samples / rjmcmc_samples (:77-155).  Every chain is an
+ * independent copy of the reference's single chain. */
+typedef struct amx_rj amx_rj;
+
+typedef struct amx_rj_stats {
+  unsigned long long acc_block, try_block;   /* runStats.naccrwmb/ntryrwmb */
+  unsigned long long acc_single, try_single; /* naccrwms/ntryrwms */
+  unsigned long long acc_jump, try_jump;     /* nacctd/ntrytd */
+  unsigned long long flops;                  /* F_RJ of SURVEY.md 8d, summed */
+  unsigned long long draws;                  /* uniforms consumed */
+  double kernel_ms;                          /* device time of the sweep kernels */
+} amx_rj_stats;
+
+/* init_flat: concatenated per-model start vectors (amSampler.initRWM).
+ * n_trace: the first n_trace chains record per-sweep (k, lp, theta, pk). */
+amx_rj *amx_rj_create(const amx_proposal *p, const amx_target *t, long nchains,
+                      const double *init_flat, uint64_t seed, int n_trace);
+void amx_rj_destroy(amx_rj *rj);
+/* Parity mode: chain c draws tape[c*stride + i] instead of its Philox stream. */
+int amx_rj_set_tape(amx_rj *rj, const double *tape, long stride);
+/* Start every chain as initChain does (one uniform picks the model). */
+int amx_rj_init_chains(amx_rj *rj);
+/* Overwrite / read the state of chains [first, first+count) (host arrays):
+ * theta count x dmax, pk count x nmodels, lp, k, nreinit, pkllim; sweep_i is
+ * shared by the population. */
+int amx_rj_set_state(amx_rj *rj, long first, long count, const double *theta,
+                     const double *pk, const double *lp, const int *k,
+                     const int *nreinit, const double *pkllim,
+                     unsigned long long sweep_i);
+int amx_rj_get_state(const amx_rj *rj, long first, long count, double *theta,
+                     double *pk, double *lp, int *k, int *nreinit,
+                     double *pkllim, unsigned long long *sweep_i);
+/* Advance every chain by nsweeps sweeps.  burning: no pk adaptation (:1258).
+ * Enqueues only; counters are valid after amx_rj_collect. */
+int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt);
+/* Wait, reduce, and read back: visits[nmodels] (64-bit model-visit counts over
+ * all chains and all sweeps since the last reset) and the counters. */
+int amx_rj_collect(amx_rj *rj, unsigned long long *visits, amx_rj_stats *st,
+                   int reset);
+/* Per-sweep records of the trace chains for the last amx_rj_sweeps call:
+ * k[n_trace*nsweeps], lp[...], theta[n_trace*nsweeps*dmax], pk[...*nmodels]. */
+int amx_rj_get_trace(const amx_rj *rj, int *k, double *lp, double *theta,
+                     double *pk);
+/* Device pointer to the 64-bit visit histogram (for a torch/NCCL all-reduce
+ * that never leaves HBM). */
+void *amx_rj_visits_dev(amx_rj *rj);
+
+/* ---- K2: Figueiredo-Jain component-wise EM mixture fit ------------------- */
+/* Replaces fit_mixture_from_samples (:664-1006) and fit_autorj (:1008-1033). */
+typedef struct amx_em_result {
+  int L;            /* components in the minimum-cost mixture */
+  int iters;        /* outer iterations performed */
+  int status;       /* 0 or AMX_ENUMERIC */
+  long comp_steps;  /* component steps performed (sum over iterations of L) */
+  double kernel_ms; /* device time of the fit kernel */
+  double flops;     /* F_EM of SURVEY.md 8d, summed over component steps */
+  double bytes;     /* 8*d bytes per sample-component-step, summed */
+} amx_em_result;
+
+/*
+ * x: n x d row-major samples.  Lmax <= AMX_MAX_COMPS start components whose
+ * means are the rows init_idx[0..Lmax) (distinct; the reference draws them by
+ * rejection from its uniform stream, :682-697 -- amx_em_draw_init reproduces
+ * that from a uniform tape).  maxit is NUM_FITMIX_MAX: maxit+1 outer iterations
+ * run when the cap binds (:961).  Outputs: wt[Lmax], mean[Lmax*d],
+ * tri[Lmax*d(d+1)/2] (first res->L valid) and per-iteration traces of capacity
+ * maxit+1 (any may be NULL): trace_L, trace_loglik, trace_cost, trace_ann.
+ * cur_* (optional) receive the working state at exit (not the best one), and
+ * cur_w the n x Lmax responsibilities, for step-parity tests.
+ */
+int amx_em_fit(int d, long n, const double *x, int Lmax, int maxit,
+               const int *init_idx, double *wt, double *mean, double *tri,
+               int *trace_L, double *trace_loglik, double *trace_cost,
+               int *trace_ann, double *cur_wt, double *cur_mean,
+               double *cur_tri, int *cur_L, double *cur_w,
+               amx_em_result *res);
+int amx_em_fit_dev(int d, long n, const double *x_dev, int Lmax, int maxit,
+                   const int *init_idx, double *wt, double *mean, double *tri,
+                   int *trace_L, double *trace_loglik, double *trace_cost,
+                   int *trace_ann, amx_em_result *res);
+/* Distinct start rows from a uniform stream exactly as :682-697; returns the
+ * number of uniforms consumed. */
+long amx_em_draw_init(long n, int Lmax, const double *uniforms, long nuniforms,
+                      int *init_idx);
+/* Single-Gaussian fit (AUTORJ_MIX_FIT). */
+int amx_autorj_fit(int d, long n, const double *x, double *wt, double *mean,
+                   double *tri);
+
+/* ---- K1: adaptive random-walk Metropolis within each model -------------- */
+/* Replaces rwm_within_model (:575-662).  One launch advances nchains
+ * independent adaptive chains of model_k for the reference's full schedule
+ * (1.1*max(nsweep2, 10000 d) sweeps); chain 0 with an injected tape is the
+ * reference chain.  samples_out: nchains x (1000 d) x d; sig_out: nchains x d. */
+int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long nchains,
+                  const double *init, uint64_t seed, const double *tape,
+                  long tape_stride, double *sig_out, double *samples_out,
+                  double *sig_trace0, double *acc_trace0, double *kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMX_H */
