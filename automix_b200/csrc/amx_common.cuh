@@ -1,0 +1,182 @@
+// amx_common.cuh -- shared host/device utilities for the automix-b200 kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "amx.h"
+
+namespace amx {
+
+// ---- host-side runtime state (amx_api.cu) -------------------------------------------
+int fail(int code, const char *fmt, ...);
+cudaStream_t stream();
+void count_launch(unsigned n = 1);
+int require_device();
+
+#define AMX_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return amx::fail(AMX_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,             \
+                       cudaGetErrorString(e_));                                          \
+  } while (0)
+
+#define AMX_CUDA_PTR(call)                                                               \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      amx::fail(AMX_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,                    \
+                cudaGetErrorString(e_));                                                 \
+      return nullptr;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+// ---- small device helpers --------------------------------------------------------------
+// The reference's max/min are macros `(A) > (B) ? (A) : (B)` (automix.c:10-11); their NaN
+// behaviour differs from fmax/fmin, and the accept rule depends on it, so mirror them.
+__device__ __forceinline__ double max_m(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double min_m(double a, double b) { return a < b ? a : b; }
+// Metropolis-Hastings acceptance probability exp(max(-30, min(0, dl))) (:612, :1063, :1247)
+__device__ __forceinline__ double mh_prob(double dl) { return exp(max_m(-30.0, min_m(0.0, dl))); }
+
+// Small arrays live in registers only if every index is a compile-time constant; these
+// accessors turn a run-time index into a select chain for small N and a plain (local
+// memory) access for large N.
+constexpr int kRegArrayMax = 8;
+
+template <int N>
+__device__ __forceinline__ double aget(const double (&a)[N], int i) {
+  if constexpr (N <= kRegArrayMax) {
+    double r = a[0];
+#pragma unroll
+    for (int j = 1; j < N; j++) r = (i == j) ? a[j] : r;
+    return r;
+  } else {
+    return a[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void aset(double (&a)[N], int i, double v) {
+  if constexpr (N <= kRegArrayMax) {
+#pragma unroll
+    for (int j = 0; j < N; j++) a[j] = (i == j) ? v : a[j];
+  } else {
+    a[i] = v;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- counter-based per-chain RNG: Philox4x32-10 ---------------------------------------
+// key = 64-bit seed, counter = (block index of this chain's stream, chain id).  One block
+// yields two 53-bit uniforms in (0,1): u = (x>>11 + 0.5) * 2^-53, never 0 or 1 (the
+// reference's generator can return exactly 0, which sends log(0) into Box-Muller;
+// SURVEY.md A.4).
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+  const unsigned long long x = ((unsigned long long)hi << 32) | lo;
+  return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct PhiloxStream {
+  uint32_t k0, k1, id0, id1;
+  unsigned long long n;  // uniforms consumed so far by this chain
+  double spare;
+  __device__ __forceinline__ void block(unsigned long long b, double &u0, double &u1) const {
+    uint32_t c[4] = {(uint32_t)b, (uint32_t)(b >> 32), id0, id1};
+    philox4x32_10(c, k0, k1);
+    u0 = u53(c[0], c[1]);
+    u1 = u53(c[2], c[3]);
+  }
+  __device__ __forceinline__ void open(unsigned long long seed, unsigned long long chain,
+                                       unsigned long long consumed) {
+    k0 = (uint32_t)seed;
+    k1 = (uint32_t)(seed >> 32);
+    id0 = (uint32_t)chain;
+    id1 = (uint32_t)(chain >> 32);
+    n = consumed;
+    spare = 0.0;
+    if (n & 1ull) {
+      double a;
+      block(n >> 1, a, spare);
+    }
+  }
+  __device__ __forceinline__ double next() {
+    double r;
+    if ((n & 1ull) == 0) {
+      block(n >> 1, r, spare);
+    } else {
+      r = spare;
+    }
+    n++;
+    return r;
+  }
+  __device__ __forceinline__ bool overrun() const { return false; }
+};
+
+// Parity mode: the chain reads an injected tape in exactly the order in which the
+// reference calls sdrand().
+struct TapeStream {
+  const double *p;
+  unsigned long long n, len;
+  bool over;
+  __device__ __forceinline__ void open(const double *tape, unsigned long long stride,
+                                       unsigned long long chain, unsigned long long consumed) {
+    p = tape + chain * stride;
+    len = stride;
+    n = consumed;
+    over = false;
+  }
+  __device__ __forceinline__ double next() {
+    double r = 0.5;
+    if (n < len) r = p[n];
+    else over = true;
+    n++;
+    return r;
+  }
+  __device__ __forceinline__ bool overrun() const { return over; }
+};
+
+// Box-Muller exactly as gauss() (automix.c:1639-1661): radius uniform first, angle second.
+template <class U>
+__device__ __forceinline__ double gauss_single(U &u) {
+  const double a = u.next(), b = u.next();
+  const double r = sqrt(-2.0 * log(a));
+  return r * sin(6.283185307179586476925 * b);
+}
+template <class U>
+__device__ __forceinline__ void gauss_pair(U &u, double &z0, double &z1) {
+  const double a = u.next(), b = u.next();
+  const double r = sqrt(-2.0 * log(a));
+  double s, c;
+  sincos(6.283185307179586476925 * b, &s, &c);
+  z0 = r * s;
+  z1 = r * c;
+}
+
+}  // namespace amx

@@ -1,0 +1,614 @@
+// amx_rj.cu -- K3 kernels and their host driver (amx_rj_* of include/amx.h).
+//
+// Mapping: one thread per chain, 128 threads per CTA.  The proposal mixtures and the
+// plug-in parameters are staged once per CTA in shared memory; a chain's state is loaded
+// once, lives in registers (small configurations) or L1-resident local memory (general
+// configuration) for all nsweeps sweeps of the launch, and is written back once.  There
+// is no per-sweep global traffic except the optional trace chains.  Model-visit counts are
+// accumulated with warp-aggregated ballots into a per-warp shared histogram and flushed with
+// one 64-bit atomic per model per CTA.
+#include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "amx_internal.cuh"
+#include "amx_rj.cuh"
+
+namespace amx {
+
+constexpr int kRjThreads = 128;
+constexpr int kRjWarps = kRjThreads / 32;
+
+__global__ void rj_gamma_kernel(double *g, unsigned long long sweep0, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // gamma = pow(1.0 / (sweep_i + 1), 2.0 / 3.0)   (automix.c:1145)
+  if (i < n) g[i] = pow(1.0 / (double)(sweep0 + (unsigned long long)i + 1ull), (2.0 / 3.0));
+}
+
+// stage [prop blob | target blob] into shared memory (8-byte words), or bind to global
+__device__ __forceinline__ void stage_blobs(const RjLaunch &a, double *smem, bool staged, const void *&pb,
+                                            const void *&tb) {
+  if (staged) {
+    const int n0 = a.prop_bytes / 8, n1 = a.tgt_bytes / 8;
+    const double *s0 = reinterpret_cast<const double *>(a.prop_blob);
+    const double *s1 = reinterpret_cast<const double *>(a.tgt_blob);
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) smem[i] = s0[i];
+    for (int i = threadIdx.x; i < n1; i += blockDim.x) smem[n0 + i] = s1[i];
+    pb = smem;
+    tb = smem + n0;
+  } else {
+    pb = a.prop_blob;
+    tb = a.tgt_blob;
+  }
+}
+
+template <class CFG>
+__device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, long id) {
+  c.k = s.k[id];
+  c.lp = s.lp[id];
+  c.pkllim = s.pkllim[id];
+  c.nreinit = s.nreinit[id];
+#pragma unroll
+  for (int i = 0; i < CFG::DMAX; i++) c.th[i] = (i < s.dmax) ? s.theta[(long)i * s.C + id] : 0.0;
+#pragma unroll
+  for (int i = 0; i < CFG::DMAX; i++) c.thn[i] = c.th[i];
+#pragma unroll
+  for (int j = 0; j < CFG::NMAX; j++) c.pk[j] = (j < s.nmodels) ? s.pk[(long)j * s.C + id] : 0.0;
+  c.acc_b = c.try_b = c.acc_s = c.try_s = c.acc_j = c.try_j = 0;
+  c.flops = 0;
+  c.kn = 0;
+  c.lr_pre = c.t_alloc = c.t_wt = c.t_det = c.gam = 0.0;
+}
+template <class CFG>
+__device__ __forceinline__ void store_chain(const ChainRegs<CFG> &c, const RjState &s, long id) {
+  s.k[id] = c.k;
+  s.lp[id] = c.lp;
+  s.pkllim[id] = c.pkllim;
+  s.nreinit[id] = c.nreinit;
+#pragma unroll
+  for (int i = 0; i < CFG::DMAX; i++)
+    if (i < s.dmax) s.theta[(long)i * s.C + id] = c.th[i];
+#pragma unroll
+  for (int j = 0; j < CFG::NMAX; j++)
+    if (j < s.nmodels) s.pk[(long)j * s.C + id] = c.pk[j];
+}
+
+template <class RNG>
+__device__ __forceinline__ void open_stream(RNG &u, const RjLaunch &a, long id, unsigned long long consumed);
+template <>
+__device__ __forceinline__ void open_stream<PhiloxStream>(PhiloxStream &u, const RjLaunch &a, long id,
+                                                          unsigned long long consumed) {
+  u.open(a.seed, a.chain_base + (unsigned long long)id, consumed);
+}
+template <>
+__device__ __forceinline__ void open_stream<TapeStream>(TapeStream &u, const RjLaunch &a, long id,
+                                                        unsigned long long consumed) {
+  u.open(a.tape, a.tape_stride, (unsigned long long)id, consumed);
+}
+
+// ---- the fused sweep kernel ------------------------------------------------------------------
+template <class CFG, class TGT, class RNG>
+__global__ void __launch_bounds__(kRjThreads) rj_sweep_kernel(RjLaunch a, int staged) {
+  extern __shared__ double smem[];
+  __shared__ unsigned s_hist[kRjWarps][CFG::NMAX];
+  __shared__ int s_clp[AMX_MAX_MODELS];
+  __shared__ unsigned long long s_cnt[8];
+  __shared__ int s_status;
+
+  const void *pb, *tb;
+  stage_blobs(a, smem, staged != 0, pb, tb);
+  for (int i = threadIdx.x; i < kRjWarps * CFG::NMAX; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_status = 0;
+  __syncthreads();
+  ProposalView P;
+  P.bind(pb);
+  TGT T;
+  T.bind(tb, a.tgt_flags);
+  const int nm = P.h->nmodels;
+  if (threadIdx.x < nm) s_clp[threadIdx.x] = T.flops(threadIdx.x);
+  __syncthreads();
+
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = gid < a.st.C;
+  const long id = active ? gid : a.st.C - 1;  // tail lanes shadow the last chain, never write
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  ChainRegs<CFG> c;
+  load_chain(c, a.st, id);
+  RNG u;
+  const unsigned long long draws0 = a.st.draws[id];
+  open_stream(u, a, id, draws0);
+  const bool traced = active && gid < a.ntrace;
+  int status = 0;
+
+  for (int s = 0; s < a.nsweeps; s++) {
+    const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
+    const int d = P.h->dims[c.k];
+    if (sweep_i % 10ull == 0ull) {  // block move every 10th sweep (:95, :148)
+      rwm_block_propose(c, P, u);
+      const double lpn = T.template eval<CFG::DMAX>(c.k, c.thn);
+      rwm_block_finish(c, P, u, lpn);
+      c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
+    } else {
+      sync_proposal(c, d);
+      for (int j = 0; j < d; j++) {
+        rwm_coord_propose(c, P, u, j);
+        const double lpn = T.template eval<CFG::DMAX>(c.k, c.thn);
+        rwm_coord_finish(c, u, j, lpn);
+      }
+      c.flops += (unsigned)(d * (s_clp[c.k] + 12));
+    }
+    rj_propose(c, P, u, a.gam[s], 0, s_clp);
+    const double lpn = T.template eval<CFG::DMAX>(c.kn, c.thn);
+    rj_finish(c, P, u, lpn, a.adapt != 0);
+    if (c.lp != c.lp) status |= 2;
+
+    // model-visit histogram: one ballot per model, lane 0 adds the population count
+    __syncwarp();
+    for (int m = 0; m < nm; m++) {
+      const unsigned b = __ballot_sync(0xffffffffu, active && c.k == m);
+      if (lane == 0) s_hist[warp][m] += __popc(b);
+    }
+    if (traced) {
+      const long row = (long)gid * a.nsweeps + s;
+      a.tr_k[row] = c.k;
+      a.tr_lp[row] = c.lp;
+      const int dk = P.h->dims[c.k];
+      for (int i = 0; i < a.st.dmax; i++) a.tr_theta[row * a.st.dmax + i] = (i < dk) ? aget(c.th, i) : 0.0;
+      for (int j = 0; j < nm; j++) a.tr_pk[row * nm + j] = aget(c.pk, j);
+    }
+  }
+  if (u.overrun()) status |= 1;
+
+  if (active) {
+    store_chain(c, a.st, id);
+    a.st.draws[id] = u.n;
+  }
+  // counters: warp reduce, one shared atomic per warp, one global atomic per CTA
+  unsigned long long v[8] = {c.acc_b, c.try_b, c.acc_s, c.try_s, c.acc_j, c.try_j, c.flops, u.n - draws0};
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const unsigned long long r = warp_sum_u64(active ? v[q] : 0ull);
+    if (lane == 0) atomicAdd(&s_cnt[q], r);
+  }
+  if (status) atomicOr(&s_status, status);
+  __syncthreads();
+  if (threadIdx.x < 8) atomicAdd(&a.cnt[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < nm) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kRjWarps; w++) t += s_hist[w][threadIdx.x];
+    atomicAdd(&a.visits[threadIdx.x], t);
+  }
+  if (threadIdx.x == 0 && s_status) atomicOr(a.status, s_status);
+}
+
+// ---- chain start (initChain, automix.c:423-449) -------------------------------------------------
+template <class TGT, class RNG>
+__global__ void __launch_bounds__(kRjThreads) rj_init_kernel(RjLaunch a, const double *init_flat) {
+  using CFG = RjCfgG;
+  ProposalView P;
+  P.bind(a.prop_blob);
+  TGT T;
+  T.bind(a.tgt_blob, a.tgt_flags);
+  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.st.C) return;
+  RNG u;
+  open_stream(u, a, id, 0ull);
+  const int nm = P.h->nmodels;
+  int k0 = (int)floor(nm * u.next());
+  if (k0 >= nm) k0 = nm - 1;
+  int off = 0;
+  for (int j = 0; j < k0; j++) off += P.h->dims[j];
+  double th[CFG::DMAX];
+  const int d = P.h->dims[k0];
+  for (int i = 0; i < CFG::DMAX; i++) th[i] = (i < d) ? init_flat[off + i] : 0.0;
+  const double lp = T.template eval<CFG::DMAX>(k0, th);
+  for (int i = 0; i < a.st.dmax; i++) a.st.theta[(long)i * a.st.C + id] = th[i];
+  for (int j = 0; j < nm; j++) a.st.pk[(long)j * a.st.C + id] = 1.0 / nm;
+  a.st.lp[id] = lp;
+  a.st.k[id] = k0;
+  a.st.nreinit[id] = 1;
+  a.st.pkllim[id] = 1.0 / 10.0;
+  a.st.draws[id] = u.n;
+  if (u.overrun()) atomicOr(a.status, 1);
+}
+
+// ---- batched evaluation of a plug-in (amx_target_eval; also the target parity tests) --------------
+template <class TGT>
+__global__ void __launch_bounds__(kRjThreads) target_eval_kernel(const void *blob, int flags, long n,
+                                                                 const int *k, const double *x, long ldx,
+                                                                 double *out) {
+  TGT T;
+  T.bind(blob, flags);
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v[AMX_MAX_DIM];
+  const int d = T.h->dims[k[i]];
+  for (int j = 0; j < AMX_MAX_DIM; j++) v[j] = (j < d) ? x[i * ldx + j] : 0.0;
+  out[i] = T.template eval<AMX_MAX_DIM>(k[i], v);
+}
+
+}  // namespace amx
+
+using namespace amx;
+
+struct amx_rj {
+  const amx_proposal *prop;
+  const amx_target *tgt;
+  long C;
+  int dmax, nm, ntrace;
+  unsigned long long seed, sweep_i, chain_base;
+  RjState st;
+  double *init_dev;
+  double *tape_dev;
+  unsigned long long tape_stride;
+  unsigned long long *visits_dev, *cnt_dev;
+  int *status_dev;
+  double *gam_dev;
+  long gam_cap;
+  int *tr_k;
+  double *tr_lp, *tr_theta, *tr_pk;
+  long tr_cap, last_nsweeps;
+  cudaEvent_t e0, e1;
+  double kernel_ms;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *pending;
+};
+
+template <class CFG, class TGT, class RNG>
+static int launch_sweeps(const RjLaunch &a) {
+  const size_t need = (size_t)a.prop_bytes + (size_t)a.tgt_bytes;
+  int staged = need <= 200 * 1024 ? 1 : 0;
+  const size_t smem = staged ? need : 0;
+  auto kern = rj_sweep_kernel<CFG, TGT, RNG>;
+  if (smem > 48 * 1024) AMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((a.st.C + kRjThreads - 1) / kRjThreads);
+  kern<<<grid, kRjThreads, smem, stream()>>>(a, staged);
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  return AMX_OK;
+}
+
+template <class TGT, class RNG>
+static int launch_cfg(const RjLaunch &a, int dmax, int Lmax, int nm) {
+  if constexpr (std::is_same<TGT, CoalTarget>::value) {
+    return launch_sweeps<RjCfgG, TGT, RNG>(a);
+  } else {
+    if (dmax <= RjCfgS::DMAX && Lmax <= RjCfgS::LMAX && nm <= RjCfgS::NMAX) return launch_sweeps<RjCfgS, TGT, RNG>(a);
+    if (dmax <= RjCfgM::DMAX && Lmax <= RjCfgM::LMAX && nm <= RjCfgM::NMAX) return launch_sweeps<RjCfgM, TGT, RNG>(a);
+    return launch_sweeps<RjCfgG, TGT, RNG>(a);
+  }
+}
+
+template <class RNG>
+static int launch_tgt(const amx_rj *rj, const RjLaunch &a) {
+  const amx_fam_hdr &h = rj->prop->hdr;
+  switch (rj->tgt->d.kind) {
+    case kTargetGaussMix: return launch_cfg<GaussMixTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
+    case kTargetQuad: return launch_cfg<QuadTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
+    case kTargetCoal: return launch_cfg<CoalTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
+  }
+  return fail(AMX_EINVAL, "plug-in kind %d has no fused sweep kernel", rj->tgt->d.kind);
+}
+
+static RjLaunch base_launch(const amx_rj *rj) {
+  RjLaunch a;
+  memset(&a, 0, sizeof(a));
+  a.st = rj->st;
+  a.prop_blob = rj->prop->blob_dev;
+  a.prop_bytes = rj->prop->blob_bytes;
+  a.tgt_blob = rj->tgt->d.blob_dev;
+  a.tgt_bytes = rj->tgt->d.blob_bytes;
+  a.tgt_flags = rj->tgt->d.flags;
+  a.seed = rj->seed;
+  a.chain_base = rj->chain_base;
+  a.tape = rj->tape_dev;
+  a.tape_stride = rj->tape_stride;
+  a.visits = rj->visits_dev;
+  a.cnt = rj->cnt_dev;
+  a.status = rj->status_dev;
+  return a;
+}
+
+extern "C" {
+
+amx_rj *amx_rj_create(const amx_proposal *p, const amx_target *t, long nchains, const double *init_flat,
+                      uint64_t seed, int n_trace) {
+  if (require_device()) return nullptr;
+  if (!p || !t || nchains < 1) {
+    fail(AMX_EINVAL, "amx_rj_create: null proposal/target or nchains<1");
+    return nullptr;
+  }
+  if (t->d.nmodels != p->hdr.nmodels) {
+    fail(AMX_EINVAL, "proposal has %d models, plug-in %d", p->hdr.nmodels, t->d.nmodels);
+    return nullptr;
+  }
+  for (int k = 0; k < p->hdr.nmodels; k++)
+    if (t->d.dims[k] != p->hdr.dims[k]) {
+      fail(AMX_EINVAL, "model %d: proposal dimension %d, plug-in %d", k, p->hdr.dims[k], t->d.dims[k]);
+      return nullptr;
+    }
+  amx_rj *rj = new amx_rj();
+  memset(rj, 0, sizeof(*rj));
+  rj->prop = p;
+  rj->tgt = t;
+  rj->C = nchains;
+  rj->dmax = p->hdr.dmax;
+  rj->nm = p->hdr.nmodels;
+  rj->seed = seed;
+  rj->sweep_i = 1;
+  rj->ntrace = n_trace < 0 ? 0 : (n_trace > nchains ? (int)nchains : n_trace);
+  RjState &s = rj->st;
+  s.C = nchains;
+  s.dmax = rj->dmax;
+  s.nmodels = rj->nm;
+  int total_d = 0;
+  for (int k = 0; k < rj->nm; k++) total_d += p->hdr.dims[k];
+  AMX_CUDA_PTR(cudaMalloc(&s.theta, sizeof(double) * (size_t)rj->dmax * nchains));
+  AMX_CUDA_PTR(cudaMalloc(&s.pk, sizeof(double) * (size_t)rj->nm * nchains));
+  AMX_CUDA_PTR(cudaMalloc(&s.lp, sizeof(double) * nchains));
+  AMX_CUDA_PTR(cudaMalloc(&s.pkllim, sizeof(double) * nchains));
+  AMX_CUDA_PTR(cudaMalloc(&s.k, sizeof(int) * nchains));
+  AMX_CUDA_PTR(cudaMalloc(&s.nreinit, sizeof(int) * nchains));
+  AMX_CUDA_PTR(cudaMalloc(&s.draws, sizeof(unsigned long long) * nchains));
+  AMX_CUDA_PTR(cudaMemsetAsync(s.draws, 0, sizeof(unsigned long long) * nchains, stream()));
+  AMX_CUDA_PTR(cudaMalloc(&rj->init_dev, sizeof(double) * total_d));
+  AMX_CUDA_PTR(cudaMemcpyAsync(rj->init_dev, init_flat, sizeof(double) * total_d, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA_PTR(cudaMalloc(&rj->visits_dev, sizeof(unsigned long long) * AMX_MAX_MODELS));
+  AMX_CUDA_PTR(cudaMalloc(&rj->cnt_dev, sizeof(unsigned long long) * 8));
+  AMX_CUDA_PTR(cudaMalloc(&rj->status_dev, sizeof(int)));
+  AMX_CUDA_PTR(cudaMemsetAsync(rj->visits_dev, 0, sizeof(unsigned long long) * AMX_MAX_MODELS, stream()));
+  AMX_CUDA_PTR(cudaMemsetAsync(rj->cnt_dev, 0, sizeof(unsigned long long) * 8, stream()));
+  AMX_CUDA_PTR(cudaMemsetAsync(rj->status_dev, 0, sizeof(int), stream()));
+  AMX_CUDA_PTR(cudaEventCreate(&rj->e0));
+  AMX_CUDA_PTR(cudaEventCreate(&rj->e1));
+  rj->pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
+  AMX_CUDA_PTR(cudaStreamSynchronize(stream()));
+  return rj;
+}
+
+void amx_rj_destroy(amx_rj *rj) {
+  if (!rj) return;
+  RjState &s = rj->st;
+  cudaFree(s.theta); cudaFree(s.pk); cudaFree(s.lp); cudaFree(s.pkllim); cudaFree(s.k);
+  cudaFree(s.nreinit); cudaFree(s.draws); cudaFree(rj->init_dev); cudaFree(rj->tape_dev);
+  cudaFree(rj->visits_dev); cudaFree(rj->cnt_dev); cudaFree(rj->status_dev); cudaFree(rj->gam_dev);
+  cudaFree(rj->tr_k); cudaFree(rj->tr_lp); cudaFree(rj->tr_theta); cudaFree(rj->tr_pk);
+  cudaEventDestroy(rj->e0);
+  cudaEventDestroy(rj->e1);
+  for (auto &pr : *rj->pending) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  delete rj->pending;
+  delete rj;
+}
+
+int amx_rj_set_chain_base(amx_rj *rj, uint64_t first_chain_id) {
+  if (!rj) return fail(AMX_EINVAL, "null handle");
+  rj->chain_base = first_chain_id;
+  return AMX_OK;
+}
+
+int amx_rj_set_tape(amx_rj *rj, const double *tape, long stride) {
+  if (!rj || !tape || stride < 1) return fail(AMX_EINVAL, "amx_rj_set_tape: bad arguments");
+  cudaFree(rj->tape_dev);
+  rj->tape_dev = nullptr;
+  const size_t nb = sizeof(double) * (size_t)stride * rj->C;
+  AMX_CUDA(cudaMalloc(&rj->tape_dev, nb));
+  AMX_CUDA(cudaMemcpyAsync(rj->tape_dev, tape, nb, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  rj->tape_stride = (unsigned long long)stride;
+  // a new tape is read from its beginning
+  AMX_CUDA(cudaMemsetAsync(rj->st.draws, 0, sizeof(unsigned long long) * rj->C, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  return AMX_OK;
+}
+
+int amx_rj_init_chains(amx_rj *rj) {
+  if (!rj) return fail(AMX_EINVAL, "null handle");
+  RjLaunch a = base_launch(rj);
+  const unsigned grid = (unsigned)((rj->C + kRjThreads - 1) / kRjThreads);
+  const bool tape = rj->tape_dev != nullptr;
+  switch (rj->tgt->d.kind) {
+    case kTargetGaussMix:
+      if (tape) rj_init_kernel<GaussMixTarget, TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      else rj_init_kernel<GaussMixTarget, PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      break;
+    case kTargetQuad:
+      if (tape) rj_init_kernel<QuadTarget, TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      else rj_init_kernel<QuadTarget, PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      break;
+    case kTargetCoal:
+      if (tape) rj_init_kernel<CoalTarget, TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      else rj_init_kernel<CoalTarget, PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      break;
+    default:
+      return fail(AMX_EINVAL, "plug-in kind %d has no device chain start", rj->tgt->d.kind);
+  }
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  rj->sweep_i = 1;
+  return AMX_OK;
+}
+
+int amx_rj_set_state(amx_rj *rj, long first, long count, const double *theta, const double *pk,
+                     const double *lp, const int *k, const int *nreinit, const double *pkllim,
+                     unsigned long long sweep_i) {
+  if (!rj || first < 0 || count < 1 || first + count > rj->C) return fail(AMX_EINVAL, "amx_rj_set_state: range");
+  RjState &s = rj->st;
+  // host arrays are chain-major; the device layout is coordinate-major
+  for (int i = 0; i < rj->dmax; i++) {
+    std::vector<double> col(count);
+    for (long c = 0; c < count; c++) col[c] = theta[c * rj->dmax + i];
+    AMX_CUDA(cudaMemcpy(s.theta + (size_t)i * rj->C + first, col.data(), sizeof(double) * count, cudaMemcpyHostToDevice));
+  }
+  for (int j = 0; j < rj->nm; j++) {
+    std::vector<double> col(count);
+    for (long c = 0; c < count; c++) col[c] = pk[c * rj->nm + j];
+    AMX_CUDA(cudaMemcpy(s.pk + (size_t)j * rj->C + first, col.data(), sizeof(double) * count, cudaMemcpyHostToDevice));
+  }
+  AMX_CUDA(cudaMemcpy(s.lp + first, lp, sizeof(double) * count, cudaMemcpyHostToDevice));
+  AMX_CUDA(cudaMemcpy(s.k + first, k, sizeof(int) * count, cudaMemcpyHostToDevice));
+  AMX_CUDA(cudaMemcpy(s.nreinit + first, nreinit, sizeof(int) * count, cudaMemcpyHostToDevice));
+  AMX_CUDA(cudaMemcpy(s.pkllim + first, pkllim, sizeof(double) * count, cudaMemcpyHostToDevice));
+  rj->sweep_i = sweep_i;
+  return AMX_OK;
+}
+
+int amx_rj_get_state(const amx_rj *rj, long first, long count, double *theta, double *pk, double *lp, int *k,
+                     int *nreinit, double *pkllim, unsigned long long *sweep_i) {
+  if (!rj || first < 0 || count < 1 || first + count > rj->C) return fail(AMX_EINVAL, "amx_rj_get_state: range");
+  const RjState &s = rj->st;
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  if (theta)
+    for (int i = 0; i < rj->dmax; i++) {
+      std::vector<double> col(count);
+      AMX_CUDA(cudaMemcpy(col.data(), s.theta + (size_t)i * rj->C + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
+      for (long c = 0; c < count; c++) theta[c * rj->dmax + i] = col[c];
+    }
+  if (pk)
+    for (int j = 0; j < rj->nm; j++) {
+      std::vector<double> col(count);
+      AMX_CUDA(cudaMemcpy(col.data(), s.pk + (size_t)j * rj->C + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
+      for (long c = 0; c < count; c++) pk[c * rj->nm + j] = col[c];
+    }
+  if (lp) AMX_CUDA(cudaMemcpy(lp, s.lp + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
+  if (k) AMX_CUDA(cudaMemcpy(k, s.k + first, sizeof(int) * count, cudaMemcpyDeviceToHost));
+  if (nreinit) AMX_CUDA(cudaMemcpy(nreinit, s.nreinit + first, sizeof(int) * count, cudaMemcpyDeviceToHost));
+  if (pkllim) AMX_CUDA(cudaMemcpy(pkllim, s.pkllim + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
+  if (sweep_i) *sweep_i = rj->sweep_i;
+  return AMX_OK;
+}
+
+int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
+  if (!rj || nsweeps < 1 || nsweeps > 2000000000L) return fail(AMX_EINVAL, "amx_rj_sweeps: bad arguments");
+  if (nsweeps > rj->gam_cap) {
+    cudaFree(rj->gam_dev);
+    rj->gam_dev = nullptr;
+    AMX_CUDA(cudaMalloc(&rj->gam_dev, sizeof(double) * nsweeps));
+    rj->gam_cap = nsweeps;
+  }
+  if (rj->ntrace > 0 && nsweeps * rj->ntrace > rj->tr_cap) {
+    cudaFree(rj->tr_k); cudaFree(rj->tr_lp); cudaFree(rj->tr_theta); cudaFree(rj->tr_pk);
+    const size_t rows = (size_t)nsweeps * rj->ntrace;
+    AMX_CUDA(cudaMalloc(&rj->tr_k, sizeof(int) * rows));
+    AMX_CUDA(cudaMalloc(&rj->tr_lp, sizeof(double) * rows));
+    AMX_CUDA(cudaMalloc(&rj->tr_theta, sizeof(double) * rows * rj->dmax));
+    AMX_CUDA(cudaMalloc(&rj->tr_pk, sizeof(double) * rows * rj->nm));
+    rj->tr_cap = (long)rows;
+  }
+  RjLaunch a = base_launch(rj);
+  a.gam = rj->gam_dev;
+  a.sweep0 = rj->sweep_i;
+  a.nsweeps = (int)nsweeps;
+  a.adapt = (do_adapt && !burning) ? 1 : 0;
+  a.ntrace = rj->ntrace;
+  a.tr_k = rj->tr_k;
+  a.tr_lp = rj->tr_lp;
+  a.tr_theta = rj->tr_theta;
+  a.tr_pk = rj->tr_pk;
+  cudaEvent_t e0, e1;
+  AMX_CUDA(cudaEventCreate(&e0));
+  AMX_CUDA(cudaEventCreate(&e1));
+  rj_gamma_kernel<<<(unsigned)((nsweeps + 255) / 256), 256, 0, stream()>>>(rj->gam_dev, rj->sweep_i, (int)nsweeps);
+  count_launch();
+  AMX_CUDA(cudaEventRecord(e0, stream()));
+  int rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
+  if (rc) return rc;
+  AMX_CUDA(cudaEventRecord(e1, stream()));
+  rj->pending->push_back({e0, e1});
+  rj->sweep_i += (unsigned long long)nsweeps;
+  rj->last_nsweeps = nsweeps;
+  return AMX_OK;
+}
+
+int amx_rj_collect(amx_rj *rj, unsigned long long *visits, amx_rj_stats *st, int reset) {
+  if (!rj) return fail(AMX_EINVAL, "null handle");
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  for (auto &pr : *rj->pending) {
+    float ms = 0;
+    AMX_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    rj->kernel_ms += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  rj->pending->clear();
+  unsigned long long cnt[8];
+  int status = 0;
+  AMX_CUDA(cudaMemcpy(cnt, rj->cnt_dev, sizeof(cnt), cudaMemcpyDeviceToHost));
+  AMX_CUDA(cudaMemcpy(&status, rj->status_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (visits) AMX_CUDA(cudaMemcpy(visits, rj->visits_dev, sizeof(unsigned long long) * rj->nm, cudaMemcpyDeviceToHost));
+  if (st) {
+    st->acc_block = cnt[0]; st->try_block = cnt[1]; st->acc_single = cnt[2]; st->try_single = cnt[3];
+    st->acc_jump = cnt[4]; st->try_jump = cnt[5]; st->flops = cnt[6]; st->draws = cnt[7];
+    st->kernel_ms = rj->kernel_ms;
+  }
+  if (reset) {
+    AMX_CUDA(cudaMemset(rj->visits_dev, 0, sizeof(unsigned long long) * AMX_MAX_MODELS));
+    AMX_CUDA(cudaMemset(rj->cnt_dev, 0, sizeof(unsigned long long) * 8));
+    AMX_CUDA(cudaMemset(rj->status_dev, 0, sizeof(int)));
+    rj->kernel_ms = 0.0;
+  }
+  if (status & 1) return fail(AMX_ETAPE, "injected uniform tape exhausted");
+  if (status & 2) return fail(AMX_ENUMERIC, "a chain reached a NaN log-posterior");
+  return AMX_OK;
+}
+
+int amx_rj_get_trace(const amx_rj *rj, int *k, double *lp, double *theta, double *pk) {
+  if (!rj || rj->ntrace < 1 || rj->last_nsweeps < 1) return fail(AMX_EINVAL, "no trace recorded");
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  const size_t rows = (size_t)rj->last_nsweeps * rj->ntrace;
+  if (k) AMX_CUDA(cudaMemcpy(k, rj->tr_k, sizeof(int) * rows, cudaMemcpyDeviceToHost));
+  if (lp) AMX_CUDA(cudaMemcpy(lp, rj->tr_lp, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+  if (theta) AMX_CUDA(cudaMemcpy(theta, rj->tr_theta, sizeof(double) * rows * rj->dmax, cudaMemcpyDeviceToHost));
+  if (pk) AMX_CUDA(cudaMemcpy(pk, rj->tr_pk, sizeof(double) * rows * rj->nm, cudaMemcpyDeviceToHost));
+  return AMX_OK;
+}
+
+void *amx_rj_visits_dev(amx_rj *rj) { return rj ? rj->visits_dev : nullptr; }
+
+int amx_target_eval(const amx_target *t, long n, const int *model_k, const double *x, long ldx, double *lp_out) {
+  if (!t || n < 1) return fail(AMX_EINVAL, "amx_target_eval: bad arguments");
+  if (t->d.kind == kTargetHostScalar) {
+    for (long i = 0; i < n; i++) lp_out[i] = t->d.scalar(model_k[i], const_cast<double *>(x) + i * ldx);
+    return AMX_OK;
+  }
+  if (t->d.kind == kTargetHostBatched) {
+    t->d.batched(n, model_k, x, ldx, lp_out, t->d.user);
+    return AMX_OK;
+  }
+  if (int rc = require_device()) return rc;
+  int *k_dev = nullptr;
+  double *x_dev = nullptr, *o_dev = nullptr;
+  AMX_CUDA(cudaMalloc(&k_dev, sizeof(int) * n));
+  AMX_CUDA(cudaMalloc(&x_dev, sizeof(double) * n * ldx));
+  AMX_CUDA(cudaMalloc(&o_dev, sizeof(double) * n));
+  AMX_CUDA(cudaMemcpyAsync(k_dev, model_k, sizeof(int) * n, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMemcpyAsync(x_dev, x, sizeof(double) * n * ldx, cudaMemcpyHostToDevice, stream()));
+  const unsigned grid = (unsigned)((n + kRjThreads - 1) / kRjThreads);
+  switch (t->d.kind) {
+    case kTargetGaussMix:
+      target_eval_kernel<GaussMixTarget><<<grid, kRjThreads, 0, stream()>>>(t->d.blob_dev, t->d.flags, n, k_dev, x_dev, ldx, o_dev);
+      break;
+    case kTargetQuad:
+      target_eval_kernel<QuadTarget><<<grid, kRjThreads, 0, stream()>>>(t->d.blob_dev, t->d.flags, n, k_dev, x_dev, ldx, o_dev);
+      break;
+    case kTargetCoal:
+      target_eval_kernel<CoalTarget><<<grid, kRjThreads, 0, stream()>>>(t->d.blob_dev, t->d.flags, n, k_dev, x_dev, ldx, o_dev);
+      break;
+  }
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  AMX_CUDA(cudaMemcpyAsync(lp_out, o_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  cudaFree(k_dev);
+  cudaFree(x_dev);
+  cudaFree(o_dev);
+  return AMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+// amx_rj.cuh -- K3: the reversible-jump sweep, one thread per chain, state on-chip for the
+// whole launch.  Device-side restatement of reversible_jump_move (automix.c:1035-1288) and
+// of the sweep loops of burn_samples / rjmcmc_samples (:77-155).
+//
+// The sweep is written as four phase functions so that the same code serves
+//   * the fused kernel (device log-posterior plug-in: one launch = nsweeps sweeps), and
+//   * the split kernels used with a host callback (propose -> host evaluates -> finish).
+#pragma once
+
+#include "amx_common.cuh"
+#include "amx_targets.cuh"
+
+namespace amx {
+
+template <int DMAX_, int LMAX_, int NMAX_>
+struct RjCfg {
+  static constexpr int DMAX = DMAX_, LMAX = LMAX_, NMAX = NMAX_;
+};
+using RjCfgS = RjCfg<2, 4, 2>;     // toy1-sized: everything in registers
+using RjCfgM = RjCfg<8, 8, 8>;     // toy2 / tutorial-sized
+using RjCfgG = RjCfg<AMX_MAX_DIM, AMX_MAX_COMPS, AMX_MAX_MODELS>;  // general (local memory)
+
+constexpr double kHalfLog2Pi = 0.9189385332046727;  // literal at automix.c:1052
+
+// Read-only view of the proposal family blob (include/amx_layout.h).
+struct ProposalView {
+  const amx_fam_hdr *h;
+  const double *D;
+  __device__ __forceinline__ void bind(const void *blob) {
+    h = reinterpret_cast<const amx_fam_hdr *>(blob);
+    D = reinterpret_cast<const double *>(h + 1);
+  }
+  __device__ __forceinline__ const double *rec(int k, int l) const { return D + h->off[k] + l * h->stride[k]; }
+  __device__ __forceinline__ const double *sig(int k) const { return D + h->ext[k]; }
+};
+
+template <class CFG>
+struct ChainRegs {
+  double th[CFG::DMAX];   // current point
+  double thn[CFG::DMAX];  // proposal
+  double pk[CFG::NMAX];   // adaptive model-jump probabilities (per chain, automix.c:1258-1282)
+  double lp;
+  double pkllim;
+  int k;
+  int nreinit;
+  // carried from rj_propose to rj_finish
+  int kn;
+  double lr_pre, t_alloc, t_wt, t_det, gam;
+  // counters (runStats, automix.h:180-185) and F_RJ accounting
+  unsigned acc_b, try_b, acc_s, try_s, acc_j, try_j;
+  unsigned long long flops;
+};
+
+// ---- within-model RWM (:1056-1085) -------------------------------------------------------
+template <class CFG, class U>
+__device__ __forceinline__ void rwm_block_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u) {
+  const int d = P.h->dims[c.k];
+  const double *sg = P.sig(c.k);
+  c.try_b++;
+  int i = 0;
+  for (; i + 1 < d; i += 2) {
+    double z0, z1;
+    gauss_pair(u, z0, z1);
+    aset(c.thn, i, fma(sg[i], z0, aget(c.th, i)));
+    aset(c.thn, i + 1, fma(sg[i + 1], z1, aget(c.th, i + 1)));
+  }
+  if (d & 1) aset(c.thn, d - 1, fma(sg[d - 1], gauss_single(u), aget(c.th, d - 1)));
+}
+template <class CFG, class U>
+__device__ __forceinline__ void rwm_block_finish(ChainRegs<CFG> &c, const ProposalView &P, U &u, double lpn) {
+  const int d = P.h->dims[c.k];
+  if (u.next() < mh_prob(lpn - c.lp)) {
+    c.acc_b++;
+    if constexpr (CFG::DMAX <= kRegArrayMax) {
+#pragma unroll
+      for (int i = 0; i < CFG::DMAX; i++) c.th[i] = (i < d) ? c.thn[i] : c.th[i];
+    } else {
+      for (int i = 0; i < d; i++) c.th[i] = c.thn[i];
+    }
+    c.lp = lpn;
+  }
+}
+// coordinate j (the caller guarantees j < d for active lanes)
+template <class CFG, class U>
+__device__ __forceinline__ void rwm_coord_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, int j) {
+  c.try_s++;
+  aset(c.thn, j, fma(P.sig(c.k)[j], gauss_single(u), aget(c.th, j)));
+}
+template <class CFG, class U>
+__device__ __forceinline__ void rwm_coord_finish(ChainRegs<CFG> &c, U &u, int j, double lpn) {
+  if (u.next() < mh_prob(lpn - c.lp)) {
+    c.acc_s++;
+    aset(c.th, j, aget(c.thn, j));
+    c.lp = lpn;
+  } else {
+    aset(c.thn, j, aget(c.th, j));
+  }
+}
+
+// allocation probabilities of point x under model k's mixture (:1094-1110 / :1217-1232)
+template <class CFG>
+__device__ __forceinline__ void alloc_probs(const ProposalView &P, int k, const double (&x)[CFG::DMAX],
+                                            double (&p)[CFG::LMAX]) {
+  const int d = P.h->dims[k], L = P.h->ncomp[k];
+  double r[CFG::DMAX];
+  double s = 0.0;
+  for (int l = 0; l < L; l++) {
+    const double *rec = P.rec(k, l);
+    const double v = exp(rec[1] + (fma(-0.5, solve_lower<CFG::DMAX>(rec, d, x, r), rec[3])));
+    aset(p, l, v);
+    s += v;
+  }
+  if (s > 0) {
+    for (int l = 0; l < L; l++) aset(p, l, aget(p, l) / s);
+  } else {
+    for (int l = 0; l < L; l++) aset(p, l, 1.0 / L);
+  }
+}
+
+// ---- between-model move, everything up to the log-posterior of the proposal -------------
+template <class CFG, class U>
+__device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, double gam,
+                                           int clp_k, const int *clp_tab) {
+  const int nm = P.h->nmodels;
+  const int k = c.k, d = P.h->dims[k], L = P.h->ncomp[k];
+  double pa[CFG::LMAX];
+  double wk[CFG::DMAX];
+  c.try_j++;
+
+  // 9.1 allocate the current point to a component (:1090-1123)
+  int l = 0;
+  double log_pa = 0.0;
+  if (L > 1) {
+    alloc_probs<CFG>(P, k, c.th, pa);
+    const double uu = u.next();
+    double t = 0.0;
+    bool found = false;
+    for (int i = 0; i < L; i++) {
+      t += aget(pa, i);
+      if (!found && uu < t) {
+        l = i;
+        found = true;
+      }
+    }
+    log_pa = log(aget(pa, l));
+    c.flops += (unsigned)(L * (d * d + 3 * d + 6));
+  }
+  // 9.2 standardise through component l (:1127-1135)
+  const double *recl = P.rec(k, l);
+  solve_lower<CFG::DMAX>(recl, d, c.th, wk);
+
+  // 9.3 proposed model and component (:1138-1169)
+  int kn = k;
+  double lr = 0.0;
+  c.gam = 0.0;
+  if (nm > 1) {
+    c.gam = gam;
+    const double uu = u.next();
+    double t = 0.0;
+    bool found = false;
+    kn = 0;
+    for (int i = 0; i < nm; i++) {
+      t += aget(c.pk, i);
+      if (!found && uu < t) {
+        kn = i;
+        found = true;
+      }
+    }
+    if (kn != k) lr = log(aget(c.pk, k)) - log(aget(c.pk, kn));
+  }
+  const int dn = P.h->dims[kn], Ln = P.h->ncomp[kn];
+  int ln = 0;
+  {
+    const double uu = u.next();
+    double t = 0.0;
+    bool found = false;
+    for (int i = 0; i < Ln; i++) {
+      t += P.rec(kn, i)[0];
+      if (!found && uu < t) {
+        ln = i;
+        found = true;
+      }
+    }
+  }
+  // 9.4 dimension matching (:1173-1204), Gaussian innovations (dof = 0, doPerm = 0)
+  if (d < dn) {
+    int i = d;
+    for (; i + 1 < dn; i += 2) {
+      double z0, z1;
+      gauss_pair(u, z0, z1);
+      aset(wk, i, z0);
+      aset(wk, i + 1, z1);
+    }
+    if ((dn - d) & 1) aset(wk, dn - 1, gauss_single(u));
+    for (int j = d; j < dn; j++) {
+      const double w = aget(wk, j);
+      lr += 0.5 * (w * w) + kHalfLog2Pi;
+    }
+  } else if (d > dn) {
+    for (int j = dn; j < d; j++) {
+      const double w = aget(wk, j);
+      lr -= (0.5 * (w * w) + kHalfLog2Pi);
+    }
+  }
+  // map through component ln of model kn (:1206-1211)
+  const double *recn = P.rec(kn, ln);
+  {
+    const double *mun = recn + AMX_REC_HEAD, *Tn = mun + 2 * dn;
+    if constexpr (CFG::DMAX <= kRegArrayMax) {
+#pragma unroll
+      for (int i = 0; i < CFG::DMAX; i++)
+        if (i < dn) {
+          double v = mun[i];
+#pragma unroll
+          for (int j = 0; j <= i; j++) v = fma(Tn[AMX_TRI(i, j)], wk[j], v);
+          c.thn[i] = v;
+        }
+    } else {
+      for (int i = 0; i < dn; i++) {
+        double v = mun[i];
+        const double *Ti = Tn + AMX_TRI(i, 0);
+        for (int j = 0; j <= i; j++) v = fma(Ti[j], wk[j], v);
+        c.thn[i] = v;
+      }
+    }
+  }
+  // 9.5 reverse allocation (:1216-1235)
+  double log_pan = 0.0;
+  if (Ln > 1) {
+    alloc_probs<CFG>(P, kn, c.thn, pa);
+    log_pan = log(aget(pa, ln));
+    c.flops += (unsigned)(Ln * (dn * dn + 3 * dn + 6));
+  }
+  c.kn = kn;
+  c.lr_pre = lr;
+  c.t_alloc = log_pan - log_pa;
+  c.t_wt = recl[1] - recn[1];
+  c.t_det = recn[2] - recl[2];
+  const int dd = d > dn ? d - dn : dn - d;
+  c.flops += (unsigned)(d * d + d + dn * dn + 2 * dn + clp_tab[kn] + 4 * dd + 4 * nm + Ln + 27);
+  (void)clp_k;
+}
+
+// 9.6 accept/reject and pk adaptation (:1238-1282).  Returns the model after the sweep.
+template <class CFG, class U>
+__device__ __forceinline__ void rj_finish(ChainRegs<CFG> &c, const ProposalView &P, U &u, double lpn,
+                                          bool adapt) {
+  const int nm = P.h->nmodels;
+  double lr = c.lr_pre;
+  lr += (lpn - c.lp);
+  lr += c.t_alloc;
+  lr += c.t_wt;
+  lr += c.t_det;
+  if (u.next() < mh_prob(lr)) {
+    const int dn = P.h->dims[c.kn];
+    if constexpr (CFG::DMAX <= kRegArrayMax) {
+#pragma unroll
+      for (int i = 0; i < CFG::DMAX; i++) c.th[i] = (i < dn) ? c.thn[i] : c.th[i];
+    } else {
+      for (int i = 0; i < dn; i++) c.th[i] = c.thn[i];
+    }
+    c.lp = lpn;
+    c.k = c.kn;
+    c.acc_j++;
+  }
+  if (adapt) {
+    bool low = false;
+    if constexpr (CFG::NMAX <= kRegArrayMax) {
+#pragma unroll
+      for (int j = 0; j < CFG::NMAX; j++)
+        if (j < nm) {
+          const double e = (j == c.k) ? 1.0 : 0.0;
+          c.pk[j] += (c.gam * (e - c.pk[j]));
+        }
+      // the reference stops at the first pk below the limit; only "any" matters
+#pragma unroll
+      for (int j = 0; j < CFG::NMAX; j++)
+        if (j < nm) low |= (c.pk[j] < c.pkllim);
+    } else {
+      for (int j = 0; j < nm; j++) {
+        const double e = (j == c.k) ? 1.0 : 0.0;
+        c.pk[j] += (c.gam * (e - c.pk[j]));
+      }
+      for (int j = 0; j < nm; j++) low |= (c.pk[j] < c.pkllim);
+    }
+    if (low) {
+      c.nreinit++;
+      c.pkllim = 1.0 / (10.0 * c.nreinit);
+      const double un = 1.0 / nm;
+      if constexpr (CFG::NMAX <= kRegArrayMax) {
+#pragma unroll
+        for (int j = 0; j < CFG::NMAX; j++) c.pk[j] = un;
+      } else {
+        for (int j = 0; j < nm; j++) c.pk[j] = un;
+      }
+    }
+  }
+}
+
+// After the accept step thn must equal th on the coordinates the next sweep touches: the
+// reference re-copies theta into thetan at the start of every component-wise sweep (:1070).
+template <class CFG>
+__device__ __forceinline__ void sync_proposal(ChainRegs<CFG> &c, int d) {
+  if constexpr (CFG::DMAX <= kRegArrayMax) {
+#pragma unroll
+    for (int i = 0; i < CFG::DMAX; i++) c.thn[i] = c.th[i];
+  } else {
+    for (int i = 0; i < d; i++) c.thn[i] = c.th[i];
+  }
+}
+
+// ---- global (SoA) chain state -------------------------------------------------------------
+struct RjState {
+  double *theta;   // [dmax][C]
+  double *pk;      // [nmodels][C]
+  double *lp;      // [C]
+  double *pkllim;  // [C]
+  int *k;          // [C]
+  int *nreinit;    // [C]
+  unsigned long long *draws;  // [C] uniforms consumed by each chain
+  long C;
+  int dmax, nmodels;
+};
+
+struct RjLaunch {
+  RjState st;
+  const void *prop_blob;
+  int prop_bytes;
+  const void *tgt_blob;
+  int tgt_bytes;
+  int tgt_flags;
+  unsigned long long seed;
+  unsigned long long chain_base;  // global id of chain 0 of this population
+  const double *tape;          // parity mode
+  unsigned long long tape_stride;
+  const double *gam;           // [nsweeps] pk-adaptation step sizes (sweep_i+1)^(-2/3)
+  unsigned long long sweep0;   // sweep_i of the first sweep of this launch
+  int nsweeps;
+  int adapt;                   // doAdapt && !isBurning
+  // outputs
+  unsigned long long *visits;  // [nmodels]
+  unsigned long long *cnt;     // [8]: 6 runStats counters, flops, draws
+  int *status;                 // bit 0: tape overrun, bit 1: NaN log-posterior
+  // trace chains
+  int ntrace;
+  int *tr_k;
+  double *tr_lp, *tr_theta, *tr_pk;
+};
+
+}  // namespace amx

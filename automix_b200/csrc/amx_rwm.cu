@@ -1,0 +1,254 @@
+// amx_rwm.cu -- K1: stage-1 adaptive random-walk Metropolis within one model.
+// Replaces rwm_within_model (automix.c:575-662).
+//
+// One thread per chain; every chain runs the reference's full adaptive schedule
+// (1.1 * max(nsweep2, 10000 d) sweeps, Robbins-Monro scale adaptation towards 25 % acceptance,
+// 10 % block moves after the first tenth, every 10th state of the last 10000 d sweeps stored),
+// so chain 0 fed an injected tape IS the reference chain, step for step.  The chains differ only
+// in their counter-based RNG stream; a whole population advances in the wall time of one chain,
+// which is what stage 2 needs when it pools the stored samples of many chains.
+#include <string.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "amx_internal.cuh"
+#include "amx_targets.cuh"
+
+namespace amx {
+
+constexpr int kRwmThreads = 128;
+
+struct RwmArgs {
+  const void *tgt_blob;
+  int tgt_flags;
+  int model_k, d;
+  int nsweepr, nburn;     // total sweeps (incl. the extra tenth), and the adaptation-only prefix
+  long nchains;
+  const double *init;     // [d]
+  const double *gtab;     // [nsweepr] 10 * (sweep+1)^(-2/3)
+  unsigned long long seed;
+  const double *tape;
+  unsigned long long tape_stride;
+  double *sig_out;      // [nchains][d]
+  double *samples_out;  // [nchains][1000 d][d]
+  double *sig_trace0, *acc_trace0;  // chain 0: [nsweepr/100][d]
+  int *status;
+};
+
+__global__ void rwm_gamma_kernel(double *g, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // gamma = 10.0 * pow(1.0 / (sweep + 1), 2.0 / 3.0), sweep = i + 1   (automix.c:619)
+  if (i < n) g[i] = 10.0 * pow(1.0 / (double)(i + 2), 2.0 / 3.0);
+}
+
+template <int DMAX, class TGT, class RNG>
+__global__ void __launch_bounds__(kRwmThreads) rwm_adapt_kernel(RwmArgs a) {
+  TGT T;
+  T.bind(a.tgt_blob, a.tgt_flags);
+  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.nchains) return;
+  const int d = a.d, k = a.model_k;
+  RNG u;
+  if constexpr (std::is_same<RNG, TapeStream>::value) u.open(a.tape, a.tape_stride, (unsigned long long)id, 0ull);
+  else u.open(a.seed, (unsigned long long)id, 0ull);
+
+  double cur[DMAX], prop[DMAX], sig[DMAX];
+  int nacc[DMAX], ntry[DMAX];
+#pragma unroll
+  for (int i = 0; i < DMAX; i++) {
+    cur[i] = prop[i] = (i < d) ? a.init[i] : 0.0;
+    sig[i] = 10.0;  // :595
+    nacc[i] = ntry[i] = 0;
+  }
+  double lp = T.template eval<DMAX>(k, cur);
+  const long nstore = 1000L * d;
+  double *out = a.samples_out + (size_t)id * nstore * d;
+  long stored = 0;
+  int ntrace = 0;
+  const double alphastar = 0.25;
+
+  for (int sweep = 1; sweep <= a.nsweepr; sweep++) {
+    const int remain = a.nsweepr - sweep;
+    const double uu = u.next();
+    if (sweep > a.nburn && uu < 0.1) {  // block move, no adaptation (:606-617)
+      int i = 0;
+      for (; i + 1 < d; i += 2) {
+        double z0, z1;
+        gauss_pair(u, z0, z1);
+        aset(prop, i, fma(aget(sig, i), z0, aget(cur, i)));
+        aset(prop, i + 1, fma(aget(sig, i + 1), z1, aget(cur, i + 1)));
+      }
+      if (d & 1) aset(prop, d - 1, fma(aget(sig, d - 1), gauss_single(u), aget(cur, d - 1)));
+      const double lpn = T.template eval<DMAX>(k, prop);
+      if (u.next() < mh_prob(lpn - lp)) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) cur[j] = prop[j];
+        lp = lpn;
+      } else {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) prop[j] = cur[j];
+      }
+    } else {  // coordinate-wise moves with scale adaptation (:618-640)
+      const double gam = a.gtab[sweep - 1];
+      for (int i = 0; i < d; i++) {
+        const double z = gauss_single(u);
+        const double si = aget(sig, i);
+        aset(prop, i, fma(si, z, aget(cur, i)));
+        const double lpn = T.template eval<DMAX>(k, prop);
+        const double acc = min_m(1.0, mh_prob(lpn - lp));
+        if (u.next() < acc) {
+          if constexpr (DMAX <= kRegArrayMax) {
+#pragma unroll
+            for (int j = 0; j < DMAX; j++) {
+              nacc[j] += (j == i);
+              ntry[j] += (j == i);
+            }
+          } else {
+            nacc[i]++;
+            ntry[i]++;
+          }
+          aset(cur, i, aget(prop, i));
+          lp = lpn;
+          aset(sig, i, max_m(0.0, si - gam * (alphastar - 1.0)));
+        } else {
+          if constexpr (DMAX <= kRegArrayMax) {
+#pragma unroll
+            for (int j = 0; j < DMAX; j++) ntry[j] += (j == i);
+          } else {
+            ntry[i]++;
+          }
+          aset(prop, i, aget(cur, i));
+          aset(sig, i, max_m(0.0, si - gam * alphastar));
+        }
+      }
+    }
+    if (remain < 10000 * d && remain % 10 == 0) {  // :642-647
+      if (stored < nstore) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++)
+          if (j < d) out[stored * d + j] = cur[j];
+      }
+      stored++;
+    }
+    if (sweep % 100 == 0) {  // :648-655
+      if (id == 0 && a.sig_trace0 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < DMAX; j++)
+          if (j < d) {
+            a.sig_trace0[(size_t)ntrace * d + j] = sig[j];
+            a.acc_trace0[(size_t)ntrace * d + j] = (double)nacc[j] / (double)ntry[j];
+          }
+      }
+      ntrace++;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < DMAX; j++)
+    if (j < d) a.sig_out[(size_t)id * d + j] = sig[j];
+  int status = 0;
+  if (u.overrun()) status |= 1;
+  if (lp != lp) status |= 2;
+  if (status) atomicOr(a.status, status);
+}
+
+template <class TGT, class RNG>
+static int rwm_launch_d(const RwmArgs &a) {
+  const unsigned grid = (unsigned)((a.nchains + kRwmThreads - 1) / kRwmThreads);
+  if constexpr (std::is_same<TGT, CoalTarget>::value) {
+    rwm_adapt_kernel<AMX_MAX_DIM, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);
+  } else {
+    if (a.d <= 2) rwm_adapt_kernel<2, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);
+    else if (a.d <= 8) rwm_adapt_kernel<8, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);
+    else rwm_adapt_kernel<AMX_MAX_DIM, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);
+  }
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  return AMX_OK;
+}
+
+template <class RNG>
+static int rwm_launch(const amx_target *t, const RwmArgs &a) {
+  switch (t->d.kind) {
+    case kTargetGaussMix: return rwm_launch_d<GaussMixTarget, RNG>(a);
+    case kTargetQuad: return rwm_launch_d<QuadTarget, RNG>(a);
+    case kTargetCoal: return rwm_launch_d<CoalTarget, RNG>(a);
+  }
+  return fail(AMX_EINVAL, "plug-in kind %d has no device RWM kernel", t->d.kind);
+}
+
+}  // namespace amx
+
+using namespace amx;
+
+extern "C" int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long nchains, const double *init,
+                             uint64_t seed, const double *tape, long tape_stride, double *sig_out,
+                             double *samples_out, double *sig_trace0, double *acc_trace0, double *kernel_ms) {
+  if (int rc = require_device()) return rc;
+  if (!t || model_k < 0 || model_k >= t->d.nmodels || nchains < 1 || nsweep2 < 1 || !init || !sig_out || !samples_out)
+    return fail(AMX_EINVAL, "amx_rwm_adapt: bad arguments");
+  const int d = t->d.dims[model_k];
+  RwmArgs a;
+  memset(&a, 0, sizeof(a));
+  int nsw = nsweep2 > 10000 * d ? nsweep2 : 10000 * d;  // :579-582
+  a.nburn = nsw / 10;
+  a.nsweepr = nsw + a.nburn;
+  a.tgt_blob = t->d.blob_dev;
+  a.tgt_flags = t->d.flags;
+  a.model_k = model_k;
+  a.d = d;
+  a.nchains = nchains;
+  a.seed = seed;
+  const long nstore = 1000L * d;
+  const int ntr = a.nsweepr / 100;
+  double *init_dev = nullptr, *gtab = nullptr, *tape_dev = nullptr, *sig_dev = nullptr, *samp_dev = nullptr,
+         *tr_dev = nullptr;
+  int *status_dev = nullptr;
+  AMX_CUDA(cudaMalloc(&init_dev, sizeof(double) * d));
+  AMX_CUDA(cudaMemcpyAsync(init_dev, init, sizeof(double) * d, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMalloc(&gtab, sizeof(double) * a.nsweepr));
+  AMX_CUDA(cudaMalloc(&sig_dev, sizeof(double) * (size_t)nchains * d));
+  AMX_CUDA(cudaMalloc(&samp_dev, sizeof(double) * (size_t)nchains * nstore * d));
+  AMX_CUDA(cudaMalloc(&tr_dev, sizeof(double) * (size_t)2 * (ntr + 1) * d));
+  AMX_CUDA(cudaMalloc(&status_dev, sizeof(int)));
+  AMX_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), stream()));
+  if (tape) {
+    AMX_CUDA(cudaMalloc(&tape_dev, sizeof(double) * (size_t)tape_stride * nchains));
+    AMX_CUDA(cudaMemcpyAsync(tape_dev, tape, sizeof(double) * (size_t)tape_stride * nchains, cudaMemcpyHostToDevice, stream()));
+  }
+  a.init = init_dev;
+  a.gtab = gtab;
+  a.tape = tape_dev;
+  a.tape_stride = (unsigned long long)tape_stride;
+  a.sig_out = sig_dev;
+  a.samples_out = samp_dev;
+  a.sig_trace0 = tr_dev;
+  a.acc_trace0 = tr_dev + (size_t)(ntr + 1) * d;
+  a.status = status_dev;
+  rwm_gamma_kernel<<<(a.nsweepr + 255) / 256, 256, 0, stream()>>>(gtab, a.nsweepr);
+  count_launch();
+  cudaEvent_t e0, e1;
+  AMX_CUDA(cudaEventCreate(&e0));
+  AMX_CUDA(cudaEventCreate(&e1));
+  AMX_CUDA(cudaEventRecord(e0, stream()));
+  int rc = tape ? rwm_launch<TapeStream>(t, a) : rwm_launch<PhiloxStream>(t, a);
+  if (rc) return rc;
+  AMX_CUDA(cudaEventRecord(e1, stream()));
+  AMX_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  AMX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  if (kernel_ms) *kernel_ms = ms;
+  int status = 0;
+  AMX_CUDA(cudaMemcpy(&status, status_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  AMX_CUDA(cudaMemcpy(sig_out, sig_dev, sizeof(double) * (size_t)nchains * d, cudaMemcpyDeviceToHost));
+  AMX_CUDA(cudaMemcpy(samples_out, samp_dev, sizeof(double) * (size_t)nchains * nstore * d, cudaMemcpyDeviceToHost));
+  if (sig_trace0) AMX_CUDA(cudaMemcpy(sig_trace0, a.sig_trace0, sizeof(double) * (size_t)ntr * d, cudaMemcpyDeviceToHost));
+  if (acc_trace0) AMX_CUDA(cudaMemcpy(acc_trace0, a.acc_trace0, sizeof(double) * (size_t)ntr * d, cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(init_dev); cudaFree(gtab); cudaFree(tape_dev); cudaFree(sig_dev); cudaFree(samp_dev); cudaFree(tr_dev);
+  cudaFree(status_dev);
+  if (status & 1) return fail(AMX_ETAPE, "injected uniform tape exhausted");
+  if (status & 2) return fail(AMX_ENUMERIC, "a chain reached a NaN log-posterior");
+  return AMX_OK;
+}

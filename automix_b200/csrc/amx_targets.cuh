@@ -1,0 +1,199 @@
+// amx_targets.cuh -- __device__ log-posterior plug-ins (the "device" tier beside the
+// reference's scalar callback `double f(int model_k, double *x)`, automix.h:46).
+//
+// A plug-in is a small view struct with
+//     template <int DMAX> double eval(int k, const double (&x)[DMAX]) const
+//     int flops(int k) const                      (C_lp of SURVEY.md 8d)
+// whose parameters sit in one contiguous blob that a CTA stages in shared memory.
+#pragma once
+
+#include <float.h>
+
+#include "amx_coal_data.h"
+#include "amx_common.cuh"
+
+namespace amx {
+
+enum TargetKind { kTargetGaussMix = 1, kTargetQuad = 2, kTargetCoal = 3, kTargetHostScalar = 100,
+                  kTargetHostBatched = 101 };
+
+// Solve T r = x - mu for the lower-triangular factor in a family record and return |r|^2.
+// (forward substitution of lnormprob, automix.c:1735-1747, with the diagonal divisions
+// replaced by multiplications with the precomputed reciprocals.)
+template <int DMAX>
+__device__ __forceinline__ double solve_lower(const double *rec, int d, const double (&x)[DMAX],
+                                              double (&r)[DMAX]) {
+  const double *mu = rec + AMX_REC_HEAD, *rd = mu + d, *T = rd + d;
+  double q = 0.0;
+  if constexpr (DMAX <= kRegArrayMax) {
+#pragma unroll
+    for (int i = 0; i < DMAX; i++) {
+      if (i < d) {
+        double v = x[i] - mu[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) v = fma(-T[AMX_TRI(i, j)], r[j], v);
+        r[i] = v * rd[i];
+        q = fma(r[i], r[i], q);
+      }
+    }
+  } else {
+    for (int i = 0; i < d; i++) {
+      double v = x[i] - mu[i];
+      const double *Ti = T + AMX_TRI(i, 0);
+      for (int j = 0; j < i; j++) v = fma(-Ti[j], r[j], v);
+      r[i] = v * rd[i];
+      q = fma(r[i], r[i], q);
+    }
+  }
+  return q;
+}
+
+// ---- Gaussian-mixture family (toy1, toy2, the synthetic scaling targets) -------------
+struct GaussMixTarget {
+  const amx_fam_hdr *h;
+  const double *D;
+  int flags;
+  __device__ __forceinline__ void bind(const void *blob, int fl) {
+    h = reinterpret_cast<const amx_fam_hdr *>(blob);
+    D = reinterpret_cast<const double *>(h + 1);
+    flags = fl;
+  }
+  __device__ __forceinline__ int flops(int k) const {
+    const int d = h->dims[k];
+    return h->ncomp[k] * (d * d + 3 * d + 6) + 2;
+  }
+  template <int DMAX>
+  __device__ __forceinline__ double eval(int k, const double (&x)[DMAX]) const {
+    const int d = h->dims[k], G = h->ncomp[k], st = h->stride[k];
+    const double *rec = D + h->off[k];
+    const double modw = D[h->ext[k]];
+    double r[DMAX];
+    if (flags == AMX_GM_PLAIN) {  // log(modw * sum_g c_g exp(-q_g/2)), as usertoy1.c:72-100
+      double s = 0.0;
+      for (int g = 0; g < G; g++) s = fma(rec[g * st + 2], exp(-0.5 * solve_lower<DMAX>(rec + g * st, d, x, r)), s);
+      return log(modw * s);
+    }
+    // log-sum-exp form: running maximum, rescale on the fly
+    double m = -DBL_MAX, s = 0.0;
+    for (int g = 0; g < G; g++) {
+      const double a = rec[g * st + 3] - 0.5 * solve_lower<DMAX>(rec + g * st, d, x, r);
+      if (a > m) {
+        s = s * exp(m - a) + 1.0;
+        m = a;
+      } else {
+        s += exp(a - m);
+      }
+    }
+    return log(modw) + m + log(s);
+  }
+};
+
+// ---- separable quadratic with box support (README 1-D Normal, truncated Normal) --------
+struct QuadTarget {
+  const amx_fam_hdr *h;  // dims[k], off[k] -> center[d], scale[d], lo[d], hi[d]
+  const double *D;
+  __device__ __forceinline__ void bind(const void *blob, int) {
+    h = reinterpret_cast<const amx_fam_hdr *>(blob);
+    D = reinterpret_cast<const double *>(h + 1);
+  }
+  __device__ __forceinline__ int flops(int k) const { return 4 * h->dims[k]; }
+  template <int DMAX>
+  __device__ __forceinline__ double eval(int k, const double (&x)[DMAX]) const {
+    const int d = h->dims[k];
+    const double *c = D + h->off[k], *sc = c + d, *lo = sc + d, *hi = lo + d;
+    double s = 0.0;
+    bool out = false;
+    if constexpr (DMAX <= kRegArrayMax) {
+#pragma unroll
+      for (int i = 0; i < DMAX; i++)
+        if (i < d) {
+          out |= (x[i] <= lo[i]) | (x[i] >= hi[i]);
+          s += -(x[i] - c[i]) * (x[i] - c[i]) / (2.0 * sc[i] * sc[i]);
+        }
+    } else {
+      for (int i = 0; i < d; i++) {
+        out |= (x[i] <= lo[i]) | (x[i] >= hi[i]);
+        s += -(x[i] - c[i]) * (x[i] - c[i]) / (2.0 * sc[i] * sc[i]);
+      }
+    }
+    return out ? -DBL_MAX : s;
+  }
+};
+
+// ---- coal-mining change-point posterior (usercpt.c:46-134) ------------------------------
+__constant__ double c_coal_y[AMX_COAL_N] = {AMX_COAL_VALUES};
+
+struct CoalTarget {
+  // blob: amx_fam_hdr (dims only) + per model [c_prior, c_tail]: the two log-gamma
+  // groups of usercpt.c:99 and :106, which depend on k alone and are formed on the host.
+  const amx_fam_hdr *h;
+  const double *D;
+  __device__ __forceinline__ void bind(const void *blob, int) {
+    h = reinterpret_cast<const amx_fam_hdr *>(blob);
+    D = reinterpret_cast<const double *>(h + 1);
+  }
+  __device__ __forceinline__ int flops(int k) const { return 12 * (k + 2) + 2 * AMX_COAL_N; }
+  template <int DMAX>
+  __device__ __forceinline__ double eval(int k, const double (&x)[DMAX]) const {
+    if constexpr (DMAX < 13) {
+      return 0.0 / 0.0;  // needs d up to 13: only the general configuration is valid
+    } else {
+      const double alpha = 1.0, beta = 200.0, T = AMX_COAL_T;
+      const int ns = k + 1;
+      double hh[8], s[9], ds[8];
+      hh[0] = x[0];
+      s[0] = 0.0;
+      for (int i = 1; i <= ns; i++) {
+        hh[i] = x[i];
+        s[i] = x[ns + i];
+        ds[i - 1] = s[i] - s[i - 1];
+      }
+      ds[ns] = T - s[ns];
+      s[ns + 1] = T;
+      bool bad = false;
+      for (int i = 0; i <= ns; i++) bad |= (hh[i] <= 0.0) | (ds[i] <= 0.0);
+      if (bad) return -10000.0;
+      const double abcon = D[h->off[k] + 2];
+      double lp = D[h->off[k] + 0];
+      for (int i = 0; i <= ns; i++) {
+        lp += (abcon + (alpha - 1.0) * log(hh[i]) - beta * hh[i]);
+        lp += log(ds[i]);
+      }
+      lp += D[h->off[k] + 1];
+      int seen = 0, j = 0;
+      double top = s[1], llh = 0.0;
+      for (int i = 0; i < AMX_COAL_N; i++) {
+        if (c_coal_y[i] > top) {  // at most one segment advance per datum (usercpt.c:114-127)
+          const int nj = i - seen;
+          seen = i;
+          llh += (nj * log(hh[j]) - hh[j] * ds[j]);
+          j++;
+          if (j > ns) return lp;
+          top = s[j + 1];
+        }
+      }
+      llh += (AMX_COAL_N - seen) * log(hh[j]) - hh[j] * ds[j];
+      return lp + llh;
+    }
+  }
+};
+
+// Host-side description of a plug-in (amx_api.cu owns these).
+struct TargetDesc {
+  int kind;
+  int flags;
+  int nmodels;
+  int dmax;
+  int dims[AMX_MAX_MODELS];
+  void *blob_dev;  // device copy of the parameter blob
+  int blob_bytes;
+  amx_scalar_fn scalar;
+  amx_batched_fn batched;
+  void *user;
+};
+
+}  // namespace amx
+
+struct amx_target {
+  amx::TargetDesc d;
+};

@@ -53,6 +53,9 @@ int amx_set_stream(void *cuda_stream);
 int amx_synchronize(void);
 /* Kernels launched by this library since the counter was last reset. */
 unsigned long long amx_launch_count(int reset);
+/* Device-to-device copy on the library stream (lets a torch tensor receive library results
+ * for an NCCL collective without a trip through the host). */
+int amx_copy_dev(void *dst_dev, const void *src_dev, size_t bytes);
 /* Dependent-free DFMA micro-benchmark: measured fp64 FLOP/s of this GPU
  * (the roofline denominator for the fp64-bound kernels). */
 int amx_measure_fp64_peak(double *flops_per_s);
@@ -135,6 +138,10 @@ typedef struct amx_rj_stats {
 amx_rj *amx_rj_create(const amx_proposal *p, const amx_target *t, long nchains,
                       const double *init_flat, uint64_t seed, int n_trace);
 void amx_rj_destroy(amx_rj *rj);
+/* Global id of this population's first chain.  The Philox stream of a chain is keyed by
+ * (seed, global chain id), so a population sharded over GPUs gives results that do not depend
+ * on the number of shards. */
+int amx_rj_set_chain_base(amx_rj *rj, uint64_t first_chain_id);
 /* Parity mode: chain c draws tape[c*stride + i] instead of its Philox stream. */
 int amx_rj_set_tape(amx_rj *rj, const double *tape, long stride);
 /* Start every chain as initChain does (one uniform picks the model). */

@@ -1,0 +1,207 @@
+"""K3 (reversible-jump sweeps) against the oracle, the reference's golden traces and, where
+oracle/_ref travelled to this box, the reference itself -- on identical injected uniforms.
+
+Bar (BASELINE.json north_star): accept decisions and model visits bit-exact, continuous state
+within 1e-12 relative."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12   # per-step bar: states re-synchronised with the checker at least every RESYNC sweeps
+DRIFT_RTOL = 1e-9  # free-running trajectories accumulate rounding (different libm, FMA); decisions stay bit-exact
+RESYNC = 40
+
+
+def _golden_mix(g):
+    return {k[4:]: g[k] for k in g if k.startswith("mix_")}
+
+
+def _close(a, b, what, rtol=RTOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    err = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    assert err.max() < rtol, (what, err.max(), int(err.argmax()))
+
+
+@pytest.mark.parametrize("name", ["toy1", "toy2"])
+def test_trace_chain_against_reference_golden(amx, name):
+    g = cases.load_golden(name)
+    wl = cases.workload(name)
+    seed = int(g["seed"][0])
+    mix = _golden_mix(g)
+    dmax = int(max(wl["dims"]))
+    n1, n2 = (int(v) for v in g["rj_nsweeps"])
+    tape = cases.tape(seed * 1000 + 999, cases.rj_tape_len(dmax, n1 + n2) + 8)
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, 3, g["init"], n_trace=3)
+    pop.set_tape(np.tile(tape, (3, 1)))  # three chains fed the same tape must stay identical
+    pop.init_chains()
+    s0 = pop.get_state()
+    assert np.all(s0["k"] == int(g["rj_init_k"][0]))
+    _close(s0["lp"], np.full(3, g["rj_init_lp"][0]), "init lp")
+    for tag, n, burning in (("burn", n1, True), ("run", n2, False)):
+        pop.sweeps(n, burning=burning)
+        vis, st = pop.collect(reset=True)
+        tr = pop.trace()
+        for c in range(3):
+            assert np.array_equal(tr["k"][c], g[f"rj_{tag}_k"]), (tag, "model sequence")
+            if tag == "burn":  # the first sweeps after the common start: per-step bar
+                _close(tr["lp"][c][:RESYNC], g[f"rj_{tag}_lp"][:RESYNC], tag + " lp (first sweeps)")
+                _close(tr["theta"][c][:RESYNC], g[f"rj_{tag}_theta"][:RESYNC], tag + " theta (first sweeps)")
+            _close(tr["lp"][c], g[f"rj_{tag}_lp"], tag + " lp", DRIFT_RTOL)
+            _close(tr["theta"][c], g[f"rj_{tag}_theta"], tag + " theta", DRIFT_RTOL)
+            _close(tr["pk"][c], g[f"rj_{tag}_pk"], tag + " pk", DRIFT_RTOL)
+        cnt = g[f"rj_{tag}_counters"]
+        got = [st[f] for f in ("acc_block", "try_block", "acc_single", "try_single", "acc_jump", "try_jump")]
+        assert got == [3 * int(v) for v in cnt], (tag, "accept counters")
+        assert np.array_equal(vis, 3 * g[f"rj_{tag}_visits"].astype(np.uint64))
+    assert st["draws"] > 0
+
+
+@pytest.mark.parametrize("name,nchains,nsweeps", [("toy1", 64, 300), ("toy2", 48, 200), ("c5_rj", 40, 120), ("c1_normal", 33, 250), ("coalmine", 24, 150)])
+def test_population_against_oracle(amx, orc, ht, name, nchains, nsweeps):
+    """Every chain gets its own tape; the oracle replays each chain on the CPU."""
+    wl = cases.workload(name)
+    spec = wl["target"]
+    ptr = ht.select(spec)
+    dims = np.asarray(wl["dims"])
+    dmax = int(dims.max())
+    init = cases.default_init(wl, 5)
+    if spec["kind"] == "gaussmix":
+        from automix_b200 import workloads as W
+
+        mix = W.ideal_proposal(wl)
+    else:  # a simple hand-made proposal: two components per model around the start point
+        wt, mean, tri, sig, ncomp = [], [], [], [], []
+        off = 0
+        for d in dims:
+            x0 = init[off:off + d]
+            off += d
+            sc = np.maximum(np.abs(x0) * 0.15, 0.05) if name == "coalmine" else np.ones(d)
+            L = 2
+            ncomp.append(L)
+            wt.append([0.6, 0.4])
+            mean.append(np.concatenate([x0, x0 + 0.5 * sc]))
+            tri.append(np.concatenate([np.diag(sc)[np.tril_indices(d)], np.diag(1.5 * sc)[np.tril_indices(d)]]))
+            sig.append(0.5 * sc)
+        mix = dict(dims=dims.astype(np.int32), ncomp=np.array(ncomp, np.int32), wt=np.concatenate(wt),
+                   mean=np.concatenate(mean), tri=np.concatenate(tri), sig=np.concatenate(sig))
+    tlen = cases.rj_tape_len(dmax, nsweeps) + 8
+    tapes = np.stack([cases.tape(1000 + c, tlen) for c in range(nchains)])
+    T, P = amx.Target(spec), amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, nchains, init, n_trace=nchains)
+    pop.set_tape(tapes)
+    pop.init_chains()
+    # the oracle replays every chain; after each segment of RESYNC sweeps the device population is
+    # re-synchronised to the oracle's states, so every compared sweep starts from identical inputs
+    states = []
+    for c in range(nchains):
+        orc.tape(tapes[c])
+        states.append(orc.chain_init(dims, init, ptr))
+    s0 = pop.get_state()
+    assert np.array_equal(s0["k"], [s["k"] for s in states])
+    _close(s0["lp"], [s["lp"] for s in states], "init lp")
+    used = [1] * nchains
+    done = 0
+    tot_vis = np.zeros(len(dims), np.int64)
+    tot_cnt = np.zeros(6, np.int64)
+    while done < nsweeps:
+        seg = min(RESYNC, nsweeps - done)
+        burning = done < nsweeps // 2
+        pop.sweeps(seg, burning=burning)
+        vis, st = pop.collect(reset=True)
+        tr = pop.trace()
+        seg_vis = np.zeros(len(dims), np.int64)
+        seg_cnt = np.zeros(6, np.int64)
+        seg_draws = 0
+        for c in range(nchains):
+            orc.tape(tapes[c][used[c]:])
+            r = orc.rj_sweeps(mix, ptr, states[c], seg, burning=burning)
+            assert not orc.tape_overrun()
+            used[c] += orc.tape_used()
+            seg_draws += orc.tape_used()
+            states[c] = r["state"]
+            assert np.array_equal(tr["k"][c], r["k"]), (c, done, "model sequence")
+            _close(tr["lp"][c], r["lp"], "lp")
+            _close(tr["theta"][c], r["theta"], "theta")
+            _close(tr["pk"][c], r["pk"], "pk")
+            seg_vis += r["visits"]
+            seg_cnt += r["counters"].astype(np.int64)
+        assert np.array_equal(vis.astype(np.int64), seg_vis)
+        got = [st[f] for f in ("acc_block", "try_block", "acc_single", "try_single", "acc_jump", "try_jump")]
+        assert got == list(seg_cnt)
+        assert st["draws"] == seg_draws, "uniforms consumed"
+        done += seg
+        fin = pop.get_state()
+        assert fin["sweep_i"] == 1 + done
+        assert np.array_equal(fin["nreinit"], [s["nreinit"] for s in states])
+        pop.set_state(states, 1 + done)
+
+
+def test_against_reference_binary_if_present(amx, po, ht):
+    if not po.have_ref():
+        pytest.skip("oracle/_ref did not travel to this box")
+    ref = po.Checker("ref")
+    g = cases.load_golden("toy1")
+    wl = cases.workload("toy1")
+    mix = _golden_mix(g)
+    ptr = ht.select(wl["target"])
+    tape = cases.tape(4242, cases.rj_tape_len(2, 800) + 8)
+    ref.tape(tape)
+    s0 = ref.chain_init(wl["dims"], g["init"], ptr)
+    r = ref.rj_sweeps(mix, ptr, s0, 800)
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, 1, g["init"], n_trace=1)
+    pop.set_tape(tape[None, :])
+    pop.init_chains()
+    pop.sweeps(800)
+    pop.collect()
+    tr = pop.trace()
+    assert np.array_equal(tr["k"][0], r["k"])
+    _close(tr["lp"][0], r["lp"], "lp")
+    _close(tr["theta"][0], r["theta"], "theta")
+
+
+def test_philox_streams_are_reproducible_and_partition_invariant(amx):
+    """Counter-based RNG keyed by (seed, chain id): the histogram for a fixed (seed, chains) must
+    not depend on how the launch is split in time, and chains must differ from one another."""
+    wl = cases.workload("toy1")
+    from automix_b200 import workloads as W
+
+    mix = W.ideal_proposal(wl)
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    init = cases.default_init(wl, 9)
+    out = []
+    for split in ((400,), (150, 250), (1, 399)):
+        pop = amx.RjPopulation(P, T, 1000, init, seed=77)
+        pop.init_chains()
+        for n in split:
+            pop.sweeps(n)
+        vis, st = pop.collect()
+        out.append((vis.copy(), st["acc_jump"], st["draws"], pop.get_state()["theta"].copy()))
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and o[1] == out[0][1] and o[2] == out[0][2]
+        assert np.array_equal(o[3], out[0][3])
+    assert len(np.unique(out[0][3][:, 0])) > 900
+    assert out[0][0].sum() == 1000 * 400
+
+
+def test_posterior_model_probabilities_toy1(amx):
+    """End-to-end statistical check: toy1's true model probabilities are 0.3 / 0.7
+    (usertoy1.c:96-100; thesis p.167 reports 0.2997 / 0.7003)."""
+    wl = cases.workload("toy1")
+    from automix_b200 import workloads as W
+
+    mix = W.ideal_proposal(wl)
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, 1 << 16, cases.default_init(wl, 3), seed=2024)
+    pop.init_chains()
+    pop.sweeps(300, burning=True)
+    pop.collect(reset=True)
+    pop.sweeps(400)
+    vis, st = pop.collect()
+    p = vis / vis.sum()
+    assert vis.sum() == (1 << 16) * 400
+    assert abs(p[0] - 0.3) < 0.004, p
+    assert 0.5 < st["acc_jump"] / st["try_jump"] <= 1.0

@@ -1,0 +1,75 @@
+"""K1 (stage-1 adaptive RWM) against the oracle and the reference's golden outputs on injected
+uniforms.  A stage-1 chain is ~1e4 d sweeps of a feedback loop (the scale adaptation), so the
+accept sequence is compared exactly and the continuous state with the drift bound; the first
+hundreds of sweeps are compared at the per-step bar."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
+
+
+@pytest.mark.parametrize("name,k", [("toy1", 0), ("toy1", 1), ("toy2", 2), ("c1_normal", 0)])
+def test_chains_against_oracle(amx, orc, ht, name, k):
+    wl = cases.workload(name)
+    ptr = ht.select(wl["target"])
+    dims = np.asarray(wl["dims"])
+    d = int(dims[k])
+    init_all = cases.default_init(wl, 8)
+    off = int(dims[:k].sum())
+    init = init_all[off:off + d]
+    nchains, nsweep2 = 5, 1000
+    tlen = cases.rwm_tape_len(d, nsweep2)
+    tapes = np.stack([cases.tape(300 + c, tlen) for c in range(nchains)])
+    T = amx.Target(wl["target"])
+    r = amx.rwm_adapt(T, k, nsweep2, nchains, init, tapes=tapes)
+    assert r["kernel_ms"] > 0
+    for c in range(nchains):
+        orc.tape(tapes[c])
+        o = orc.rwm_within_model(k, d, nsweep2, ptr, init)
+        assert not orc.tape_overrun()
+        # the stored samples repeat while proposals are rejected: identical repeat pattern == identical accepts
+        rep_dev = np.all(r["samples"][c][1:] == r["samples"][c][:-1], axis=1)
+        rep_orc = np.all(o["samples"][1:] == o["samples"][:-1], axis=1)
+        assert np.array_equal(rep_dev, rep_orc), "accept pattern differs"
+        assert _rel(r["samples"][c], o["samples"]) < 1e-9
+        assert _rel(r["sig"][c], o["sig"]) < 1e-9
+        if c == 0:
+            assert _rel(r["sig_trace"][:5], o["sig_trace"][:5]) < 1e-12  # first 500 sweeps: per-step bar
+            assert _rel(r["sig_trace"], o["sig_trace"]) < 1e-9
+            assert np.allclose(r["acc_trace"], o["acc_trace"], rtol=0, atol=1e-15, equal_nan=True)
+
+
+def test_against_reference_golden(amx):
+    g = cases.load_golden("toy1")
+    wl = cases.workload("toy1")
+    seed = int(g["seed"][0])
+    T = amx.Target(wl["target"])
+    off = 0
+    for k, d in enumerate(wl["dims"]):
+        d = int(d)
+        tape = cases.tape(seed * 1000 + 2 * k, cases.rwm_tape_len(d, 1000))
+        r = amx.rwm_adapt(T, k, 1000, 1, g["init"][off:off + d], tapes=tape[None, :])
+        off += d
+        assert _rel(r["sig"][0], g[f"rwm{k}_sig"]) < 1e-9
+        assert _rel(r["samples"][0][:64], g[f"rwm{k}_samples_head"]) < 1e-9
+        assert _rel(r["samples"][0][-64:], g[f"rwm{k}_samples_tail"]) < 1e-9
+        assert _rel(r["sig_trace"][::10], g[f"rwm{k}_sig_trace"]) < 1e-9
+
+
+def test_philox_population_statistics(amx):
+    """256 independent adaptive chains on the README Normal(0.5, 1): pooled stored samples must have
+    the right mean / sd, and the adapted scales must agree across chains."""
+    wl = cases.workload("c1_normal")
+    T = amx.Target(wl["target"])
+    r = amx.rwm_adapt(T, 0, 10000, 256, wl["init"], seed=5)
+    x = r["samples"].reshape(-1)
+    assert abs(x.mean() - 0.5) < 0.02 and abs(x.std() - 1.0) < 0.02
+    assert 0.2 < r["sig"].std() / r["sig"].mean() < 1.0 or r["sig"].std() < 2.0
+    assert len(np.unique(r["samples"][:, -1, 0])) > 200
