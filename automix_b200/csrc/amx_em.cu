@@ -222,7 +222,10 @@ __device__ void em_plan_step(EmCtrl *c, const EmArgs &a) {
     c->comp_steps++;
     c->flops += (double)a.n * (2.0 * d * d + 8.0 * d + 4.0 * c->L + 7.0);
     if (c->lam[cc] > 0.005) {
-      for (int j = 0; j < d; j++) c->mu[cc][j] = c->S1[j] / c->colsum[cc];
+      for (int j = 0; j < d; j++) {
+        c->mu[cc][j] = c->S1[j] / c->colsum[cc];
+        c->rec[AMX_REC_HEAD + j] = c->mu[cc][j];  // the scatter pass centres on the NEW mean (:803-809)
+      }
       c->pass = kPassScatter;
       return;
     }

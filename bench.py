@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- the headline metric of BASELINE.json on B200: chain-sweeps/s of the reversible-jump
+sweep kernel (primary line) and EM-fit samples/s of the mixture fit (the "em" object of the same
+line), beside the reference's CPU code on the same box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  RJ : every chain of the population advances --sweeps sweeps (one fused kernel launch)
+  EM : one Figueiredo-Jain fit of n samples for --em-maxit+1 outer iterations (one kernel launch)
+Workloads: C2 = toy1 targets (usertoy1.c), 2 models d=1,2, with the mixtures the
+reference fitted (tests/golden/toy1.npz) as jump proposals; C5-EM = 1e6 samples, d=10, Lmax=30.
+Chains are independent, so N GPUs = N shards with no per-step traffic (weak scaling: chains per
+GPU fixed); the 64-bit model-visit histogram is all-reduced once (NCCL) inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=1 << 20, help="chains per GPU")
+    ap.add_argument("--sweeps", type=int, default=200, help="sweeps per step")
+    ap.add_argument("--em-n", type=int, default=1_000_000)
+    ap.add_argument("--em-d", type=int, default=10)
+    ap.add_argument("--em-L", type=int, default=30)
+    ap.add_argument("--em-maxit", type=int, default=20)
+    ap.add_argument("--em-steps", type=int, default=3)
+    ap.add_argument("--no-em", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="toy1", choices=["toy1", "toy2", "c5_rj", "c1_normal"])
+    return ap.parse_args()
+
+
+def golden_mix(name):
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", name + ".npz")))
+    return {k[4:]: g[k] for k in g if k.startswith("mix_")}, g["init"]
+
+
+def workload(args):
+    from automix_b200 import workloads as W
+
+    wl = getattr(W, args.workload)()
+    if args.workload in ("toy1", "toy2"):
+        mix, init = golden_mix(args.workload)
+        desc = "proposal = mixtures fitted by the reference (tests/golden/%s.npz)" % args.workload
+    elif args.workload == "c5_rj":
+        mix, init = W.ideal_proposal(wl), wl["init"]
+        desc = "proposal = the targets' own components"
+    else:
+        mix = dict(dims=np.array([1], np.int32), ncomp=np.array([1], np.int32), wt=np.array([1.0]),
+                   mean=np.array([0.5]), tri=np.array([1.05]), sig=np.array([4.9]))
+        init, desc = wl["init"], "proposal = the mixture the reference fits (SURVEY.md appendix C)"
+    return wl, mix, np.asarray(init, np.float64), desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hot = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(hot)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_bench
+    from automix_b200 import workloads as W
+
+    wl, mix, init, desc = workload(args)
+    per_step = 1_000_000  # sweeps per process per step: ~2 s of CPU work per core on toy1
+    vals, t_steps = [], []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = cpu_bench.rj_baseline(wl["target"], mix, init, 10000, per_step)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            vals.append(r["value"]); t_steps.append(dt)
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "chain-sweeps/s", "value": value, "unit": "chain-sweeps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(t_steps)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C2 {args.workload}: {desc}; reference CPU code, one process per host core"},
+            "cpu_baseline": {"value": value, "unit": "chain-sweeps/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if not args.no_em:
+        x, _ = W.c5_em_samples(n=20000, d=args.em_d, seed=2025)
+        e = cpu_bench.em_baseline(x, args.em_L, 0)
+        line["em"] = {"metric": "EM-fit samples/s", "value": e["value"], "unit": "EM-fit samples/s",
+                      "cpu_baseline": {k: e[k] for k in ("value", "unit", "cores", "kind", "sample")}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from automix_b200 import _lib as amx
+    from automix_b200 import workloads as W
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    amx.check(amx.lib().amx_set_device(local))
+    amx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ RJ sweeps (primary metric)
+    wl, mix, init, desc = workload(args)
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    C, S = args.chains, args.sweeps
+    nm = len(mix["dims"])
+    pop = amx.RjPopulation(P, T, C, init, seed=20261018)
+    pop.set_chain_base(rank * C)
+    pop.init_chains()
+    pop.sweeps(1000, burning=True)  # burn-in: the chains forget the common start
+    pop.collect(reset=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    hist = torch.zeros(nm, dtype=torch.int64, device=dev)
+    fp64_peak = amx.measure_fp64_peak() if rank == 0 else 0.0
+
+    for _ in range(args.warmup):
+        pop.sweeps(S)
+    pop.collect(reset=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    barrier()
+    amx.launch_count(reset=True)
+    if rank == 0:
+        clocks.start()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()  # L2 flush between timed steps (outside the per-step event pair)
+        ev[s][0].record(stream)
+        pop.sweeps(S)
+        ev[s][1].record(stream)
+    pop.visits_to(hist.data_ptr())
+    if world > 1:
+        dist.all_reduce(hist)  # the one collective of the path: final model-visit histogram
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop() if rank == 0 else None
+    launches = amx.launch_count()
+    vis_local, st = pop.collect(reset=False)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = torch.tensor([sum(step_ms) * 1e-3, t_wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    t_rj, t_rj_wall = (float(v) for v in t_dev.cpu())
+    total_sweeps = float(world) * C * S * args.steps
+    value = total_sweeps / t_rj
+    hist_h = hist.cpu().numpy()
+    assert int(hist_h.sum()) == int(total_sweeps), "model-visit histogram does not add up"
+    flops = torch.tensor([float(st["flops"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(flops)
+    roof_rj = None
+    if rank == 0:
+        ach = float(st["flops"]) / (st["kernel_ms"] * 1e-3)  # this rank's dominant kernel, per-launch average
+        roof_rj = {"bound": "fp64", "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                   "frac": ach / fp64_peak, "traffic": None,
+                   "kernel": "rj_sweep_kernel", "launch_ms": st["kernel_ms"] / args.steps,
+                   "flops_per_sweep": float(st["flops"]) / (C * S * args.steps),
+                   "peak_source": "measured live with amx_measure_fp64_peak (dependent-free DFMA loop); "
+                                  "MEASURED_PEAKS.json has no fp64 entry (SURVEY.md 8d)",
+                   "note": "algorithmic F_RJ flops of SURVEY.md 8d (exp/log/sqrt/sincos count as 1 flop each)"}
+
+    # end-to-end through the C-ABI with host buffers: H2D of the inputs, the sweeps, D2H of the result
+    e2e = None
+    if True:
+        e2e_steps = max(2, min(args.steps, 5))
+        init_pin = torch.from_numpy(init.copy()).pin_memory()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for s in range(e2e_steps):
+            P2 = amx.Proposal(mix)                       # H2D: proposal blob
+            T2 = amx.Target(wl["target"])                # H2D: plug-in parameters
+            pop2 = amx.RjPopulation(P2, T2, C, init_pin.numpy(), seed=7 + s)  # H2D: start vectors
+            pop2.set_chain_base(rank * C)
+            pop2.init_chains()
+            pop2.sweeps(S)
+            v2, st2 = pop2.collect()                     # D2H: histogram + counters
+            fin = pop2.get_state()                       # D2H: every chain's final state (the posterior sample)
+            d2h = sum(a.nbytes for a in fin.values() if hasattr(a, "nbytes")) + v2.nbytes + 72
+            pop2.close(); T2.close(); P2.close()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = int(P.mix["wt"].nbytes + P.mix["mean"].nbytes + P.mix["tri"].nbytes + P.mix["sig"].nbytes + init.nbytes + 2048)
+        e2e = {"value": float(world) * C * S * e2e_steps / float(te.cpu()[0]), "unit": "chain-sweeps/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+               "what": "per step: create proposal + plug-in + population from host arrays, chain start, "
+                       f"{S} sweeps, read back histogram, counters and all {C} final chain states"}
+    pop.close()
+    del flush
+
+    # ------------------------------------------------------------------ EM fit (second metric)
+    em = None
+    if not args.no_em and rank == 0:
+        n, d, L = args.em_n, args.em_d, args.em_L
+        x, _ = W.c5_em_samples(n=n, d=d, seed=2025)
+        idx, _ = amx.em_draw_init(n, L, W.splitmix_uniforms_fast(99, 4096))
+        x_pin = torch.from_numpy(x).pin_memory()
+        x_dev = x_pin.to(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        r = None
+        for _ in range(2):
+            r = amx.em_fit(x, idx, Lmax=L, maxit=args.em_maxit, x_dev_ptr=x_dev.data_ptr())
+        ms, steps_, its = [], 0, 0
+        amx.launch_count(reset=True)
+        for _ in range(args.em_steps):
+            r = amx.em_fit(x, idx, Lmax=L, maxit=args.em_maxit, x_dev_ptr=x_dev.data_ptr())
+            ms.append(r["kernel_ms"]); steps_ = r["comp_steps"]; its = r["iters"]
+        em_launches = amx.launch_count()
+        t_fit = float(np.mean(ms)) * 1e-3
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = 8.0 * d * n * steps_
+        stream_bytes = 8.0 * n * steps_ * (2 * d + L + 3)  # upper bound of what the two passes move (L = Lmax)
+        t0 = time.perf_counter()
+        e2e_fits = 2
+        for _ in range(e2e_fits):
+            r2 = amx.em_fit(x_pin.numpy(), idx, Lmax=L, maxit=args.em_maxit)  # H2D of x inside
+        t_e2e = (time.perf_counter() - t0) / e2e_fits
+        em = {"metric": "EM-fit samples/s", "value": n * its / t_fit, "unit": "EM-fit samples/s",
+              "ms_per_fit": 1e3 * t_fit, "outer_iterations": its, "component_steps": int(steps_),
+              "sample_component_steps_per_s": n * steps_ / t_fit, "final_L": int(r["L"]),
+              "config": {"workload": f"C5-EM: n={n} samples, d={d}, Lmax={L}, NUM_FITMIX_MAX={args.em_maxit} "
+                                     f"({its} outer iterations), 6-component synthetic mixture (seed 2025); "
+                                     "inputs (80 MB) + density cache (240 MB) exceed L2, no flush needed"},
+              "roofline": {"bound": "hbm", "achieved": alg_bytes / t_fit / 1e9, "peak": hbm, "unit": "GB/s",
+                           "frac": alg_bytes / t_fit / 1e9 / hbm, "traffic": None,
+                           "kernel": "em_fit_kernel", "launch_ms": 1e3 * t_fit,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                           "note": "algorithmic bytes = 8 d per sample-component-step (SURVEY.md 8d)",
+                           "streamed_model_GBs": stream_bytes / t_fit / 1e9,
+                           "fp64": {"achieved": r["flops"] / t_fit / 1e12, "peak": fp64_peak / 1e12,
+                                    "frac": r["flops"] / t_fit / fp64_peak, "unit": "TFLOP/s",
+                                    "note": "F_EM = 2d^2+8d+4L+7 flops per sample-component-step"}},
+              "e2e": {"value": n * r2["iters"] / t_e2e, "unit": "EM-fit samples/s",
+                      "h2d_bytes_per_step": int(x.nbytes + 4 * L), "d2h_bytes_per_step": int(8 * L * (1 + d + d * (d + 1) // 2) + 24 * its)},
+              "gpu_launches": int(em_launches)}
+        del x_dev
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import cpu_bench
+
+        cpu = cpu_bench.rj_baseline(wl["target"], mix, init, 10000, 4_000_000)
+        if em is not None:
+            xs, _ = W.c5_em_samples(n=20000, d=args.em_d, seed=2025)
+            e = cpu_bench.em_baseline(xs, args.em_L, 1)
+            em["cpu_baseline"] = {k: e[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "chain-sweeps/s", "value": value, "unit": "chain-sweeps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_rj / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"C2 {args.workload} (usertoy1.c targets: 2 models, d=1,2): {C} chains/GPU x {S} sweeps/step; {desc}",
+                           "chains_per_gpu": C, "sweeps_per_step": S, "rng": "Philox4x32-10 keyed by (seed, global chain id)",
+                           "l2": "256 MiB write between timed steps (outside the per-step event pairs); chain state is read once per launch",
+                           "timing": "sum of per-step CUDA-event pairs on the launching stream, max over ranks",
+                           "wall_s_incl_flush_and_allreduce": t_rj_wall},
+                "roofline": roof_rj, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "model_probs": (hist_h / hist_h.sum()).round(5).tolist(),
+                "accept_rate_jump": st["acc_jump"] / max(1, st["try_jump"])}
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["per_core"] = cpu["per_core"]
+        if em is not None:
+            line["em"] = em
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
