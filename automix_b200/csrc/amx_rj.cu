@@ -186,6 +186,160 @@ __global__ void __launch_bounds__(kRjThreads) rj_sweep_kernel(RjLaunch a, int st
   if (threadIdx.x == 0 && s_status) atomicOr(a.status, s_status);
 }
 
+
+// ---- split sweep for HOST log-posterior callbacks -------------------------------------------------
+// The scalar contract `double f(int model_k, double *x)` (automix.h:46) can only run on the host.
+// A sweep then becomes a sequence of small kernels -- propose | host evaluates | finish -- built from
+// the same phase functions as the fused kernel; chain state, proposals and the values carried from
+// rj_propose to rj_finish live in global memory between them.  Compatibility path: (d+1) PCIe round
+// trips per sweep, regardless of the number of chains.
+enum RjPhase { kPhBlockPropose = 0, kPhBlockFinish, kPhCoordPropose, kPhCoordFinish, kPhJumpPropose, kPhJumpFinish };
+
+struct RjSplit {
+  double *thn;    // [C][dmax] chain-major: what the host callback reads
+  int *keval;     // [C] model index to evaluate, -1 = this chain sits the phase out
+  double *lpn;    // [C] values returned by the callback
+  int *kn;        // [C]
+  double *carry;  // [5][C]: lr_pre, t_alloc, t_wt, t_det, gam
+};
+
+template <class RNG>
+__global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSplit sp, int phase, int j, int s) {
+  using CFG = RjCfgG;
+  __shared__ int s_clp[AMX_MAX_MODELS];
+  __shared__ unsigned s_hist[kRjWarps][CFG::NMAX];
+  __shared__ unsigned long long s_cnt[8];
+  ProposalView P;
+  P.bind(a.prop_blob);
+  const int nm = P.h->nmodels;
+  if (threadIdx.x < AMX_MAX_MODELS) s_clp[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < kRjWarps * CFG::NMAX; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = gid < a.st.C;
+  const long id = active ? gid : a.st.C - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  ChainRegs<CFG> c;
+  load_chain(c, a.st, id);
+  const int dmax = a.st.dmax;
+  for (int i = 0; i < dmax; i++) c.thn[i] = sp.thn[id * dmax + i];
+  c.kn = sp.kn[id];
+  c.lr_pre = sp.carry[0 * a.st.C + id];
+  c.t_alloc = sp.carry[1 * a.st.C + id];
+  c.t_wt = sp.carry[2 * a.st.C + id];
+  c.t_det = sp.carry[3 * a.st.C + id];
+  c.gam = sp.carry[4 * a.st.C + id];
+  RNG u;
+  const unsigned long long draws0 = a.st.draws[id];
+  open_stream(u, a, id, draws0);
+  const int d = P.h->dims[c.k];
+  const double lpn = sp.lpn[id];
+  int keval = -1;
+  switch (phase) {
+    case kPhBlockPropose:
+      rwm_block_propose(c, P, u);
+      keval = c.k;
+      break;
+    case kPhBlockFinish:
+      rwm_block_finish(c, P, u, lpn);
+      break;
+    case kPhCoordPropose:
+      if (j == 0) sync_proposal(c, d);
+      if (j < d) {
+        rwm_coord_propose(c, P, u, j);
+        keval = c.k;
+      }
+      break;
+    case kPhCoordFinish:
+      if (j < d) rwm_coord_finish(c, u, j, lpn);
+      break;
+    case kPhJumpPropose:
+      rj_propose(c, P, u, a.gam[s], 0, s_clp);
+      keval = c.kn;
+      break;
+    case kPhJumpFinish:
+      rj_finish(c, P, u, lpn, a.adapt != 0);
+      break;
+  }
+  int status = (u.overrun() ? 1 : 0) | ((c.lp != c.lp) ? 2 : 0);
+  if (phase == kPhJumpFinish) {
+    __syncwarp();
+    for (int m = 0; m < nm; m++) {
+      const unsigned b = __ballot_sync(0xffffffffu, active && c.k == m);
+      if (lane == 0) s_hist[warp][m] += __popc(b);
+    }
+    if (active && gid < a.ntrace) {
+      const long row = (long)gid * a.nsweeps + s;
+      a.tr_k[row] = c.k;
+      a.tr_lp[row] = c.lp;
+      const int dk = P.h->dims[c.k];
+      for (int i = 0; i < dmax; i++) a.tr_theta[row * dmax + i] = (i < dk) ? c.th[i] : 0.0;
+      for (int q = 0; q < nm; q++) a.tr_pk[row * nm + q] = c.pk[q];
+    }
+  }
+  if (active) {
+    store_chain(c, a.st, id);
+    a.st.draws[id] = u.n;
+    for (int i = 0; i < dmax; i++) sp.thn[id * dmax + i] = c.thn[i];
+    sp.keval[id] = keval;
+    sp.kn[id] = c.kn;
+    sp.carry[0 * a.st.C + id] = c.lr_pre;
+    sp.carry[1 * a.st.C + id] = c.t_alloc;
+    sp.carry[2 * a.st.C + id] = c.t_wt;
+    sp.carry[3 * a.st.C + id] = c.t_det;
+    sp.carry[4 * a.st.C + id] = c.gam;
+  }
+  unsigned long long v[8] = {c.acc_b, c.try_b, c.acc_s, c.try_s, c.acc_j, c.try_j, 0ull, u.n - draws0};
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const unsigned long long r = warp_sum_u64(active ? v[q] : 0ull);
+    if (lane == 0) atomicAdd(&s_cnt[q], r);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&a.cnt[threadIdx.x], s_cnt[threadIdx.x]);
+  if (phase == kPhJumpFinish && threadIdx.x < nm) {
+    unsigned long long t = 0;
+    for (int w = 0; w < kRjWarps; w++) t += s_hist[w][threadIdx.x];
+    atomicAdd(&a.visits[threadIdx.x], t);
+  }
+  if (status && active) atomicOr(a.status, status);
+}
+
+// chain start for host callbacks: pick the model and copy the start vector; lp comes from the host
+template <class RNG>
+__global__ void __launch_bounds__(kRjThreads) rj_init_split_kernel(RjLaunch a, RjSplit sp, const double *init_flat,
+                                                                   int finish) {
+  ProposalView P;
+  P.bind(a.prop_blob);
+  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.st.C) return;
+  const int nm = P.h->nmodels, dmax = a.st.dmax;
+  if (finish) {
+    a.st.lp[id] = sp.lpn[id];
+    return;
+  }
+  RNG u;
+  open_stream(u, a, id, 0ull);
+  int k0 = (int)floor(nm * u.next());
+  if (k0 >= nm) k0 = nm - 1;
+  int off = 0;
+  for (int q = 0; q < k0; q++) off += P.h->dims[q];
+  const int d = P.h->dims[k0];
+  for (int i = 0; i < dmax; i++) {
+    const double v = (i < d) ? init_flat[off + i] : 0.0;
+    a.st.theta[(long)i * a.st.C + id] = v;
+    sp.thn[id * dmax + i] = v;
+  }
+  for (int q = 0; q < nm; q++) a.st.pk[(long)q * a.st.C + id] = 1.0 / nm;
+  a.st.k[id] = k0;
+  a.st.nreinit[id] = 1;
+  a.st.pkllim[id] = 1.0 / 10.0;
+  a.st.draws[id] = u.n;
+  sp.keval[id] = k0;
+  if (u.overrun()) atomicOr(a.status, 1);
+}
+
 // ---- chain start (initChain, automix.c:423-449) -------------------------------------------------
 template <class TGT, class RNG>
 __global__ void __launch_bounds__(kRjThreads) rj_init_kernel(RjLaunch a, const double *init_flat) {
@@ -256,6 +410,12 @@ struct amx_rj {
   cudaEvent_t e0, e1;
   double kernel_ms;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *pending;
+  // host-callback mode
+  RjSplit sp;
+  double *h_thn, *h_lpn;  // pinned mirrors
+  int *h_keval;
+  std::vector<int> *h_kc;
+  std::vector<double> *h_xc, *h_lc;
 };
 
 template <class CFG, class TGT, class RNG>
@@ -311,6 +471,94 @@ static RjLaunch base_launch(const amx_rj *rj) {
   a.cnt = rj->cnt_dev;
   a.status = rj->status_dev;
   return a;
+}
+
+
+static bool is_host_target(const amx_rj *rj) {
+  return rj->tgt->d.kind == kTargetHostScalar || rj->tgt->d.kind == kTargetHostBatched;
+}
+
+static int split_alloc(amx_rj *rj) {
+  if (rj->sp.thn) return AMX_OK;
+  const size_t C = (size_t)rj->C;
+  AMX_CUDA(cudaMalloc(&rj->sp.thn, sizeof(double) * C * rj->dmax));
+  AMX_CUDA(cudaMalloc(&rj->sp.keval, sizeof(int) * C));
+  AMX_CUDA(cudaMalloc(&rj->sp.lpn, sizeof(double) * C));
+  AMX_CUDA(cudaMalloc(&rj->sp.kn, sizeof(int) * C));
+  AMX_CUDA(cudaMalloc(&rj->sp.carry, sizeof(double) * 5 * C));
+  AMX_CUDA(cudaMemset(rj->sp.thn, 0, sizeof(double) * C * rj->dmax));
+  AMX_CUDA(cudaMemset(rj->sp.lpn, 0, sizeof(double) * C));
+  AMX_CUDA(cudaMemset(rj->sp.kn, 0, sizeof(int) * C));
+  AMX_CUDA(cudaMemset(rj->sp.carry, 0, sizeof(double) * 5 * C));
+  AMX_CUDA(cudaMallocHost(&rj->h_thn, sizeof(double) * C * rj->dmax));
+  AMX_CUDA(cudaMallocHost(&rj->h_lpn, sizeof(double) * C));
+  AMX_CUDA(cudaMallocHost(&rj->h_keval, sizeof(int) * C));
+  rj->h_kc = new std::vector<int>();
+  rj->h_xc = new std::vector<double>();
+  rj->h_lc = new std::vector<double>();
+  return AMX_OK;
+}
+
+// proposals -> host, callback on the chains that take part in this phase, values -> device
+static int split_evaluate(amx_rj *rj) {
+  const size_t C = (size_t)rj->C;
+  const int dmax = rj->dmax;
+  AMX_CUDA(cudaMemcpyAsync(rj->h_thn, rj->sp.thn, sizeof(double) * C * dmax, cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaMemcpyAsync(rj->h_keval, rj->sp.keval, sizeof(int) * C, cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  const TargetDesc &t = rj->tgt->d;
+  if (t.kind == kTargetHostScalar) {
+    for (size_t c = 0; c < C; c++)
+      if (rj->h_keval[c] >= 0) rj->h_lpn[c] = t.scalar(rj->h_keval[c], rj->h_thn + c * dmax);
+  } else {
+    std::vector<int> &kc = *rj->h_kc;
+    std::vector<double> &xc = *rj->h_xc, &lc = *rj->h_lc;
+    kc.clear();
+    xc.clear();
+    for (size_t c = 0; c < C; c++)
+      if (rj->h_keval[c] >= 0) {
+        kc.push_back(rj->h_keval[c]);
+        xc.insert(xc.end(), rj->h_thn + c * dmax, rj->h_thn + (c + 1) * dmax);
+      }
+    lc.resize(kc.size());
+    if (!kc.empty()) t.batched((long)kc.size(), kc.data(), xc.data(), dmax, lc.data(), t.user);
+    size_t q = 0;
+    for (size_t c = 0; c < C; c++)
+      if (rj->h_keval[c] >= 0) rj->h_lpn[c] = lc[q++];
+  }
+  AMX_CUDA(cudaMemcpyAsync(rj->sp.lpn, rj->h_lpn, sizeof(double) * C, cudaMemcpyHostToDevice, stream()));
+  return AMX_OK;
+}
+
+static int split_phase(amx_rj *rj, const RjLaunch &a, int phase, int j, int s) {
+  const unsigned grid = (unsigned)((rj->C + kRjThreads - 1) / kRjThreads);
+  if (rj->tape_dev) rj_split_kernel<TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->sp, phase, j, s);
+  else rj_split_kernel<PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->sp, phase, j, s);
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  return AMX_OK;
+}
+
+static int split_sweeps(amx_rj *rj, RjLaunch &a) {
+  if (int rc = split_alloc(rj)) return rc;
+  for (int s = 0; s < a.nsweeps; s++) {
+    const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
+    int rc = 0;
+    if (sweep_i % 10ull == 0ull) {
+      if ((rc = split_phase(rj, a, kPhBlockPropose, 0, s)) || (rc = split_evaluate(rj)) ||
+          (rc = split_phase(rj, a, kPhBlockFinish, 0, s)))
+        return rc;
+    } else {
+      for (int j = 0; j < rj->dmax; j++)
+        if ((rc = split_phase(rj, a, kPhCoordPropose, j, s)) || (rc = split_evaluate(rj)) ||
+            (rc = split_phase(rj, a, kPhCoordFinish, j, s)))
+          return rc;
+    }
+    if ((rc = split_phase(rj, a, kPhJumpPropose, 0, s)) || (rc = split_evaluate(rj)) ||
+        (rc = split_phase(rj, a, kPhJumpFinish, 0, s)))
+      return rc;
+  }
+  return AMX_OK;
 }
 
 extern "C" {
@@ -384,6 +632,13 @@ void amx_rj_destroy(amx_rj *rj) {
     cudaEventDestroy(pr.second);
   }
   delete rj->pending;
+  cudaFree(rj->sp.thn); cudaFree(rj->sp.keval); cudaFree(rj->sp.lpn); cudaFree(rj->sp.kn); cudaFree(rj->sp.carry);
+  if (rj->h_thn) cudaFreeHost(rj->h_thn);
+  if (rj->h_lpn) cudaFreeHost(rj->h_lpn);
+  if (rj->h_keval) cudaFreeHost(rj->h_keval);
+  delete rj->h_kc;
+  delete rj->h_xc;
+  delete rj->h_lc;
   delete rj;
 }
 
@@ -413,6 +668,19 @@ int amx_rj_init_chains(amx_rj *rj) {
   RjLaunch a = base_launch(rj);
   const unsigned grid = (unsigned)((rj->C + kRjThreads - 1) / kRjThreads);
   const bool tape = rj->tape_dev != nullptr;
+  if (is_host_target(rj)) {
+    if (int rc = split_alloc(rj)) return rc;
+    for (int finish = 0; finish < 2; finish++) {
+      if (tape) rj_init_split_kernel<TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->sp, rj->init_dev, finish);
+      else rj_init_split_kernel<PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->sp, rj->init_dev, finish);
+      count_launch();
+      AMX_CUDA(cudaGetLastError());
+      if (!finish)
+        if (int rc = split_evaluate(rj)) return rc;
+    }
+    rj->sweep_i = 1;
+    return AMX_OK;
+  }
   switch (rj->tgt->d.kind) {
     case kTargetGaussMix:
       if (tape) rj_init_kernel<GaussMixTarget, TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
@@ -517,7 +785,9 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
   rj_gamma_kernel<<<(unsigned)((nsweeps + 255) / 256), 256, 0, stream()>>>(rj->gam_dev, rj->sweep_i, (int)nsweeps);
   count_launch();
   AMX_CUDA(cudaEventRecord(e0, stream()));
-  int rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
+  int rc;
+  if (is_host_target(rj)) rc = split_sweeps(rj, a);
+  else rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
   if (rc) return rc;
   AMX_CUDA(cudaEventRecord(e1, stream()));
   rj->pending->push_back({e0, e1});

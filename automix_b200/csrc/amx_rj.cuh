@@ -16,7 +16,7 @@ template <int DMAX_, int LMAX_, int NMAX_>
 struct RjCfg {
   static constexpr int DMAX = DMAX_, LMAX = LMAX_, NMAX = NMAX_;
 };
-using RjCfgS = RjCfg<2, 4, 2>;     // toy1-sized: everything in registers
+using RjCfgS = RjCfg<2, 8, 2>;     // toy1-sized: everything in registers
 using RjCfgM = RjCfg<8, 8, 8>;     // toy2 / tutorial-sized
 using RjCfgG = RjCfg<AMX_MAX_DIM, AMX_MAX_COMPS, AMX_MAX_MODELS>;  // general (local memory)
 

@@ -152,6 +152,126 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_adapt_kernel(RwmArgs a) {
   if (status) atomicOr(a.status, status);
 }
 
+
+// ---- split form for HOST log-posterior callbacks ---------------------------------------------------
+// Same chain, cut at every log-posterior evaluation: kernel j of a sweep finishes proposal j-1 with
+// the value the host returned and makes proposal j.  State lives in global memory between kernels.
+struct RwmSplit {
+  double *cur, *prop, *sig;  // [C][d] chain-major (prop is what the host callback reads)
+  int *nacc, *ntry;          // [C][d]
+  double *lp, *lpn;          // [C]
+  int *mode, *keval;         // [C] mode: 1 = block move this sweep
+  long *stored;              // [C]
+  unsigned long long *draws; // [C]
+};
+
+template <class RNG>
+__global__ void __launch_bounds__(kRwmThreads) rwm_split_kernel(RwmArgs a, RwmSplit sp, int sweep, int j) {
+  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= a.nchains) return;
+  const int d = a.d, k = a.model_k;
+  RNG u;
+  if constexpr (std::is_same<RNG, TapeStream>::value) u.open(a.tape, a.tape_stride, (unsigned long long)id, sp.draws[id]);
+  else u.open(a.seed, (unsigned long long)id, sp.draws[id]);
+  double *cur = sp.cur + id * d, *prop = sp.prop + id * d, *sig = sp.sig + id * d;
+  int *nacc = sp.nacc + id * d, *ntry = sp.ntry + id * d;
+  const double alphastar = 0.25;
+  int keval = -1;
+  if (sweep == 0) {  // chain start: the host evaluates the start point (:599)
+    if (j == 0) {
+      for (int i = 0; i < d; i++) {
+        cur[i] = prop[i] = a.init[i];
+        sig[i] = 10.0;
+        nacc[i] = ntry[i] = 0;
+      }
+      sp.stored[id] = 0;
+      sp.mode[id] = 0;
+      keval = k;
+    } else {
+      sp.lp[id] = sp.lpn[id];
+    }
+    sp.keval[id] = keval;
+    return;
+  }
+  double lp = sp.lp[id];
+  const double lpn = sp.lpn[id];
+  int mode = sp.mode[id];
+  // ---- finish the proposal made by the previous kernel of this sweep
+  if (j > 0) {
+    if (mode == 1) {
+      if (j == 1) {
+        if (u.next() < mh_prob(lpn - lp)) {
+          for (int i = 0; i < d; i++) cur[i] = prop[i];
+          lp = lpn;
+        } else {
+          for (int i = 0; i < d; i++) prop[i] = cur[i];
+        }
+      }
+    } else {
+      const int i = j - 1;
+      const double gam = a.gtab[sweep - 1];
+      const double acc = min_m(1.0, mh_prob(lpn - lp));
+      if (u.next() < acc) {
+        nacc[i]++;
+        ntry[i]++;
+        cur[i] = prop[i];
+        lp = lpn;
+        sig[i] = max_m(0.0, sig[i] - gam * (alphastar - 1.0));
+      } else {
+        ntry[i]++;
+        prop[i] = cur[i];
+        sig[i] = max_m(0.0, sig[i] - gam * alphastar);
+      }
+    }
+  }
+  // ---- make the next proposal, or close the sweep
+  if (j == 0) {
+    const double uu = u.next();
+    mode = (sweep > a.nburn && uu < 0.1) ? 1 : 0;
+    if (mode == 1) {
+      int i = 0;
+      for (; i + 1 < d; i += 2) {
+        double z0, z1;
+        gauss_pair(u, z0, z1);
+        prop[i] = fma(sig[i], z0, cur[i]);
+        prop[i + 1] = fma(sig[i + 1], z1, cur[i + 1]);
+      }
+      if (d & 1) prop[d - 1] = fma(sig[d - 1], gauss_single(u), cur[d - 1]);
+    } else {
+      prop[0] = fma(sig[0], gauss_single(u), cur[0]);
+    }
+    keval = k;
+  } else if (j < d) {
+    if (mode == 0) {
+      prop[j] = fma(sig[j], gauss_single(u), cur[j]);
+      keval = k;
+    }
+  } else {  // j == d: end of sweep (:642-655)
+    const int remain = a.nsweepr - sweep;
+    if (remain < 10000 * d && remain % 10 == 0) {
+      const long st = sp.stored[id];
+      if (st < 1000L * d)
+        for (int i = 0; i < d; i++) a.samples_out[((size_t)id * 1000 * d + st) * d + i] = cur[i];
+      sp.stored[id] = st + 1;
+    }
+    if (sweep % 100 == 0 && id == 0 && a.sig_trace0 != nullptr) {
+      const int row = sweep / 100 - 1;
+      for (int i = 0; i < d; i++) {
+        a.sig_trace0[(size_t)row * d + i] = sig[i];
+        a.acc_trace0[(size_t)row * d + i] = (double)nacc[i] / (double)ntry[i];
+      }
+    }
+    if (sweep == a.nsweepr)
+      for (int i = 0; i < d; i++) a.sig_out[(size_t)id * d + i] = sig[i];
+  }
+  sp.lp[id] = lp;
+  sp.mode[id] = mode;
+  sp.keval[id] = keval;
+  sp.draws[id] = u.n;
+  int status = (u.overrun() ? 1 : 0) | ((lp != lp) ? 2 : 0);
+  if (status) atomicOr(a.status, status);
+}
+
 template <class TGT, class RNG>
 static int rwm_launch_d(const RwmArgs &a) {
   const unsigned grid = (unsigned)((a.nchains + kRwmThreads - 1) / kRwmThreads);
@@ -175,6 +295,80 @@ static int rwm_launch(const amx_target *t, const RwmArgs &a) {
     case kTargetCoal: return rwm_launch_d<CoalTarget, RNG>(a);
   }
   return fail(AMX_EINVAL, "plug-in kind %d has no device RWM kernel", t->d.kind);
+}
+
+
+static int rwm_host_run(const amx_target *t, RwmArgs &a) {
+  const size_t C = (size_t)a.nchains;
+  const int d = a.d;
+  RwmSplit sp;
+  memset(&sp, 0, sizeof(sp));
+  AMX_CUDA(cudaMalloc(&sp.cur, sizeof(double) * C * d));
+  AMX_CUDA(cudaMalloc(&sp.prop, sizeof(double) * C * d));
+  AMX_CUDA(cudaMalloc(&sp.sig, sizeof(double) * C * d));
+  AMX_CUDA(cudaMalloc(&sp.nacc, sizeof(int) * C * d));
+  AMX_CUDA(cudaMalloc(&sp.ntry, sizeof(int) * C * d));
+  AMX_CUDA(cudaMalloc(&sp.lp, sizeof(double) * C));
+  AMX_CUDA(cudaMalloc(&sp.lpn, sizeof(double) * C));
+  AMX_CUDA(cudaMalloc(&sp.mode, sizeof(int) * C));
+  AMX_CUDA(cudaMalloc(&sp.keval, sizeof(int) * C));
+  AMX_CUDA(cudaMalloc(&sp.stored, sizeof(long) * C));
+  AMX_CUDA(cudaMalloc(&sp.draws, sizeof(unsigned long long) * C));
+  AMX_CUDA(cudaMemsetAsync(sp.draws, 0, sizeof(unsigned long long) * C, stream()));
+  AMX_CUDA(cudaMemsetAsync(sp.lpn, 0, sizeof(double) * C, stream()));
+  double *h_prop = nullptr, *h_lpn = nullptr;
+  int *h_keval = nullptr;
+  AMX_CUDA(cudaMallocHost(&h_prop, sizeof(double) * C * d));
+  AMX_CUDA(cudaMallocHost(&h_lpn, sizeof(double) * C));
+  AMX_CUDA(cudaMallocHost(&h_keval, sizeof(int) * C));
+  std::vector<int> kc;
+  std::vector<double> xc, lc;
+  const unsigned grid = (unsigned)((C + kRwmThreads - 1) / kRwmThreads);
+  auto launch = [&](int sweep, int j) -> int {
+    if (a.tape) rwm_split_kernel<TapeStream><<<grid, kRwmThreads, 0, stream()>>>(a, sp, sweep, j);
+    else rwm_split_kernel<PhiloxStream><<<grid, kRwmThreads, 0, stream()>>>(a, sp, sweep, j);
+    count_launch();
+    AMX_CUDA(cudaGetLastError());
+    return AMX_OK;
+  };
+  auto evaluate = [&]() -> int {
+    AMX_CUDA(cudaMemcpyAsync(h_prop, sp.prop, sizeof(double) * C * d, cudaMemcpyDeviceToHost, stream()));
+    AMX_CUDA(cudaMemcpyAsync(h_keval, sp.keval, sizeof(int) * C, cudaMemcpyDeviceToHost, stream()));
+    AMX_CUDA(cudaStreamSynchronize(stream()));
+    if (t->d.kind == kTargetHostScalar) {
+      for (size_t c = 0; c < C; c++)
+        if (h_keval[c] >= 0) h_lpn[c] = t->d.scalar(h_keval[c], h_prop + c * d);
+    } else {
+      kc.clear();
+      xc.clear();
+      for (size_t c = 0; c < C; c++)
+        if (h_keval[c] >= 0) {
+          kc.push_back(h_keval[c]);
+          xc.insert(xc.end(), h_prop + c * d, h_prop + (c + 1) * d);
+        }
+      lc.resize(kc.size());
+      if (!kc.empty()) t->d.batched((long)kc.size(), kc.data(), xc.data(), d, lc.data(), t->d.user);
+      size_t q = 0;
+      for (size_t c = 0; c < C; c++)
+        if (h_keval[c] >= 0) h_lpn[c] = lc[q++];
+    }
+    AMX_CUDA(cudaMemcpyAsync(sp.lpn, h_lpn, sizeof(double) * C, cudaMemcpyHostToDevice, stream()));
+    return AMX_OK;
+  };
+  int rc = 0;
+  if ((rc = launch(0, 0)) || (rc = evaluate()) || (rc = launch(0, 1))) return rc;
+  for (int sweep = 1; sweep <= a.nsweepr && !rc; sweep++) {
+    for (int j = 0; j < d && !rc; j++) {
+      rc = launch(sweep, j);
+      if (!rc) rc = evaluate();
+    }
+    if (!rc) rc = launch(sweep, d);
+  }
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  cudaFree(sp.cur); cudaFree(sp.prop); cudaFree(sp.sig); cudaFree(sp.nacc); cudaFree(sp.ntry); cudaFree(sp.lp);
+  cudaFree(sp.lpn); cudaFree(sp.mode); cudaFree(sp.keval); cudaFree(sp.stored); cudaFree(sp.draws);
+  cudaFreeHost(h_prop); cudaFreeHost(h_lpn); cudaFreeHost(h_keval);
+  return rc;
 }
 
 }  // namespace amx
@@ -231,7 +425,9 @@ extern "C" int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long
   AMX_CUDA(cudaEventCreate(&e0));
   AMX_CUDA(cudaEventCreate(&e1));
   AMX_CUDA(cudaEventRecord(e0, stream()));
-  int rc = tape ? rwm_launch<TapeStream>(t, a) : rwm_launch<PhiloxStream>(t, a);
+  int rc;
+  if (t->d.kind == kTargetHostScalar || t->d.kind == kTargetHostBatched) rc = rwm_host_run(t, a);
+  else rc = tape ? rwm_launch<TapeStream>(t, a) : rwm_launch<PhiloxStream>(t, a);
   if (rc) return rc;
   AMX_CUDA(cudaEventRecord(e1, stream()));
   AMX_CUDA(cudaEventSynchronize(e1));

@@ -1,0 +1,186 @@
+/*
+ * test_dropin.c -- end-to-end checks of the drop-in LibAutoMix API (include/automix.h) in the
+ * style of the reference's own test program (tests/test_automix.c there): every case is the
+ * pipeline initAMSampler -> estimate_conditional_probs -> burn_samples -> rjmcmc_samples with a
+ * user callback `double f(int, double*)`, followed by a statistical check on am.st.*.
+ * The scenarios are ours (same families: samplers, parameter estimation, two-model selection);
+ * tolerances are tighter than the reference's +-0.5 where Monte-Carlo error allows.
+ *
+ * Build: gcc tests/c/test_dropin.c -Iinclude -Lautomix_b200/lib -lautomix -lm
+ */
+#include "automix.h"
+#include "amx.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+static int failures = 0;
+#define CHECK(cond, ...)                              \
+  do {                                                \
+    if (!(cond)) {                                    \
+      failures++;                                     \
+      printf("  FAIL %s:%d: ", __FILE__, __LINE__);   \
+      printf(__VA_ARGS__);                            \
+      printf("\n");                                   \
+    }                                                 \
+  } while (0)
+
+static const double ydata[10] = {0.50613293, 0.70961096, 0.28166951, 0.12532996, 0.46374168,
+                                 0.58337466, 0.52458217, 0.56052633, 0.57215576, 0.68698825};
+
+/* N(0.5, 1) up to a constant */
+static double lp_normal(int k, double *x) { (void)k; return -(x[0] - 0.5) * (x[0] - 0.5) / 2.0; }
+/* N(1, 1) truncated to (0, 10) */
+static double lp_truncnormal(int k, double *x) {
+  (void)k;
+  if (x[0] <= 0.0 || x[0] >= 10.0) return -DBL_MAX;
+  return -(x[0] - 1.0) * (x[0] - 1.0) / 2.0;
+}
+/* Beta(2, 2) through the exported loggamma */
+static double lp_beta22(int k, double *x) {
+  (void)k;
+  if (x[0] <= 0.0 || x[0] >= 1.0) return -DBL_MAX;
+  return log(x[0]) + log(1.0 - x[0]) + loggamma(4.0) - 2.0 * loggamma(2.0);
+}
+/* likelihood of ydata under N(mu, sigma), theta = (sigma, mu) */
+static double lp_normal_params(int k, double *t) {
+  (void)k;
+  if (t[0] <= 0.0) return -DBL_MAX;
+  double s = 0.0;
+  for (int i = 0; i < 10; i++) s += -(ydata[i] - t[1]) * (ydata[i] - t[1]);
+  return -10.0 * log(t[0]) + s / (2.0 * t[0] * t[0]);
+}
+/* likelihood of ydata under Beta(a, b) */
+static double lp_beta_params(int k, double *t) {
+  (void)k;
+  if (t[0] <= 0.0 || t[1] <= 0.0) return -DBL_MAX;
+  double s = 0.0;
+  for (int i = 0; i < 10; i++) s += (t[0] - 1.0) * log(ydata[i]) + (t[1] - 1.0) * log(1.0 - ydata[i]);
+  return s + 10.0 * (loggamma(t[0] + t[1]) - loggamma(t[0]) - loggamma(t[1]));
+}
+static double lp_normal_vs_beta(int k, double *t) { return k == 0 ? lp_normal_params(0, t) : lp_beta_params(1, t); }
+
+static void run_pipeline(amSampler *am, int nmodels, int *dims, targetDist f, double *init, int nrj) {
+  int rc = initAMSampler(am, nmodels, dims, f, init);
+  CHECK(rc == EXIT_SUCCESS, "initAMSampler returned %d", rc);
+  amx_sampler_set_seed(am, 20261018u);
+  amx_sampler_set_chains(am, 64, 1);
+  estimate_conditional_probs(am, 20000);
+  burn_samples(am, 2000);
+  rjmcmc_samples(am, nrj);
+  const amx_sampler_stats *s = amx_sampler_stats_get(am);
+  CHECK(s && s->last_error == 0, "GPU stage failed: %s", amx_last_error());
+}
+
+static void moments_1d(amSampler *am, int k, int comp, double *mean, double *sd, double *lo, double *hi) {
+  int n = am->st.theta_summary_len[k];
+  double s = 0, ss = 0;
+  *lo = DBL_MAX;
+  *hi = -DBL_MAX;
+  for (int i = 0; i < n; i++) {
+    double v = am->st.theta_summary[k][i][comp];
+    s += v;
+    ss += v * v;
+    if (v < *lo) *lo = v;
+    if (v > *hi) *hi = v;
+  }
+  *mean = s / n;
+  *sd = sqrt(ss / n - (*mean) * (*mean));
+}
+
+static void test_sampler(const char *name, targetDist f, double init0, double mean, double sd, double lo, double hi) {
+  printf("%s ...\n", name);
+  amSampler am;
+  int d = 1;
+  double init[1] = {init0};
+  const int n = 20000;
+  run_pipeline(&am, 1, &d, f, init, n);
+  double m, s, a, b;
+  CHECK(am.st.ksummary && am.st.ksummary[0] == n, "ksummary[0]=%d", am.st.ksummary ? am.st.ksummary[0] : -1);
+  CHECK(am.st.theta_summary_len[0] == n, "theta_summary_len");
+  moments_1d(&am, 0, 0, &m, &s, &a, &b);
+  printf("  mean %.4f (want %.4f)  sd %.4f (want %.4f)  range [%.3f, %.3f]  L=%d sig=%.3f\n", m, mean, s, sd, a, b,
+         am.jd.nMixComps[0], am.jd.sig[0][0]);
+  CHECK(fabs(m - mean) < 0.08, "mean");
+  CHECK(fabs(s - sd) < 0.08, "sd");
+  CHECK(a > lo && b < hi, "support");
+  for (int i = 0; i < n; i += 997) CHECK(am.st.k_which_summary[i] == 1, "k_which_summary is 1-based");
+  CHECK(am.cpstats.nfitmix[0] > 0 && am.cpstats.fitmix_Lkk[0][am.cpstats.nfitmix[0] - 1] >= 1, "EM trace");
+  CHECK(am.st.timesecs_rjmcmc > 0 && am.cpstats.timesecs_condprobs > 0, "timers");
+  CHECK(am.ch.sweep_i == 1u + 2000u + (unsigned long)n, "sweep_i persists across burn -> sample (%lu)", am.ch.sweep_i);
+  freeAMSampler(&am);
+}
+
+static void test_two_models(void) {
+  printf("Normal-vs-Beta model selection ...\n");
+  amSampler am;
+  int dims[2] = {2, 2};
+  double init[4] = {0.2, 0.5, 3.0, 3.0};
+  const int n = 30000;
+  run_pipeline(&am, 2, dims, lp_normal_vs_beta, init, n);
+  const amx_sampler_stats *s = amx_sampler_stats_get(&am);
+  double tot = (double)(s->visits[0] + s->visits[1]);
+  double frac_pop = s->visits[0] / tot;
+  double frac0 = am.st.ksummary[0] / (double)n;
+  double m_sig, m_mu, sd, lo, hi;
+  moments_1d(&am, 0, 0, &m_sig, &sd, &lo, &hi);
+  moments_1d(&am, 0, 1, &m_mu, &sd, &lo, &hi);
+  printf("  P(normal) chain0 %.3f, population %.3f (reference test expects 0.95 +- 0.5); sigma %.3f mu %.3f\n", frac0,
+         frac_pop, m_sig, m_mu);
+  CHECK(tot == 64.0 * n, "population visits add up (%g)", tot);
+  CHECK(frac_pop > 0.85 && frac_pop < 0.995, "posterior model probability");
+  CHECK(fabs(frac0 - frac_pop) < 0.05, "chain 0 agrees with the population");
+  CHECK(fabs(m_mu - 0.5) < 0.05 && fabs(m_sig - 0.21) < 0.06, "posterior means of (sigma, mu)");
+  CHECK(am.st.ntrytd == 64ul * n, "jump tries");
+  freeAMSampler(&am);
+}
+
+static void test_device_plugin(void) {
+  printf("toy1 with the __device__ Gaussian-mixture plug-in ...\n");
+  int dims[2] = {1, 2}, ncomp[2] = {2, 3};
+  double modw[2] = {0.3, 0.7};
+  double wt[5] = {0.2, 0.8, 1.0 / 3, 1.0 / 3, 1.0 / 3};
+  double mean[8] = {-3, 2, 0, 3, -4, 1, 4, 1};
+  double tri[11] = {2, 1, 2, 0, 0.7071068, 1.414214, 1.060660, 0.9354143, 1.414214, -1.060660, 0.9354143};
+  amx_target *t = amx_target_gaussmix(2, dims, ncomp, modw, wt, mean, tri, AMX_GM_PLAIN);
+  CHECK(t != NULL, "amx_target_gaussmix: %s", amx_last_error());
+  amSampler am;
+  double init[3] = {0.3, -0.2, 0.4};
+  initAMSampler(&am, 2, dims, NULL, init);
+  amx_sampler_set_target(&am, t);
+  amx_sampler_set_seed(&am, 99);
+  amx_sampler_set_chains(&am, 32768, 1);
+  estimate_conditional_probs(&am, 100000);
+  burn_samples(&am, 1000);
+  rjmcmc_samples(&am, 2000);
+  const amx_sampler_stats *s = amx_sampler_stats_get(&am);
+  double p0 = s->visits[0] / (double)(s->visits[0] + s->visits[1]);
+  printf("  fitted L = (%d, %d); P(model 1) = %.4f (true 0.3; thesis 0.2997)\n", am.jd.nMixComps[0], am.jd.nMixComps[1], p0);
+  CHECK(s->last_error == 0, "GPU stage failed: %s", amx_last_error());
+  CHECK(fabs(p0 - 0.3) < 0.01, "posterior model probability");
+  CHECK(am.jd.nMixComps[0] >= 1 && am.jd.nMixComps[1] >= 2, "mixture fit");
+  freeAMSampler(&am);
+  amx_target_destroy(t);
+}
+
+int main(void) {
+  amSampler bad;
+  int d1 = 1;
+  printf("negative nmodels ...\n");
+  CHECK(initAMSampler(&bad, -1, &d1, lp_normal, NULL) == EXIT_FAILURE, "negative nmodels must fail");
+  unsigned long seed = 12345;
+  sdrni(&seed);
+  double u0 = sdrand();
+  CHECK(fabs(u0 - 0.25515066366218653) < 1e-16, "sdrand after sdrni(12345) = %.17g", u0);
+  CHECK(fabs(loggamma(7.25) - 7.0521854507385395) < 1e-13, "loggamma");
+
+  test_sampler("Normal(0.5,1) sampler", lp_normal, 0.5, 0.5, 1.0, -DBL_MAX, DBL_MAX);
+  test_sampler("truncated Normal sampler", lp_truncnormal, 1.0, 1.2876, 0.7939, 0.0, 10.0);
+  test_sampler("Beta(2,2) sampler", lp_beta22, 0.5, 0.5, 0.2236, 0.0, 1.0);
+  test_two_models();
+  test_device_plugin();
+  printf(failures ? "FAILED (%d)\n" : "OK\n", failures);
+  return failures ? 1 : 0;
+}

@@ -205,3 +205,39 @@ def test_posterior_model_probabilities_toy1(amx):
     assert vis.sum() == (1 << 16) * 400
     assert abs(p[0] - 0.3) < 0.004, p
     assert 0.5 < st["acc_jump"] / st["try_jump"] <= 1.0
+
+
+@pytest.mark.parametrize("mode", ["scalar", "batched"])
+def test_host_callback_mode_against_oracle(amx, orc, ht, mode):
+    """The reference's scalar callback contract (and the batched variant) through the split
+    propose | host evaluates | finish kernels: same tape, same answers as the oracle."""
+    wl = cases.workload("toy2")
+    ptr = ht.select(wl["target"])
+    g = cases.load_golden("toy2")
+    mix = _golden_mix(g)
+    dims = np.asarray(wl["dims"])
+    nchains, nsweeps = 6, 60
+    tapes = np.stack([cases.tape(7000 + c, cases.rj_tape_len(5, nsweeps) + 8) for c in range(nchains)])
+    T = amx.Target(wl["target"], host_fn=ht.ptr) if mode == "scalar" else amx.Target(wl["target"], host_batched=ht.batched_ptr)
+    P = amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, nchains, g["init"], n_trace=nchains)
+    pop.set_tape(tapes)
+    pop.init_chains()
+    pop.sweeps(nsweeps // 2, burning=True)
+    pop.collect(reset=True)
+    tr1 = pop.trace()
+    pop.sweeps(nsweeps - nsweeps // 2)
+    vis, st = pop.collect()
+    tr2 = pop.trace()
+    tot = np.zeros(len(dims), np.int64)
+    for c in range(nchains):
+        orc.tape(tapes[c])
+        s0 = orc.chain_init(dims, g["init"], ptr)
+        a = orc.rj_sweeps(mix, ptr, s0, nsweeps // 2, burning=True)
+        b = orc.rj_sweeps(mix, ptr, a["state"], nsweeps - nsweeps // 2)
+        assert np.array_equal(tr1["k"][c], a["k"]) and np.array_equal(tr2["k"][c], b["k"])
+        _close(tr2["lp"][c], b["lp"], "lp")
+        _close(tr2["theta"][c], b["theta"], "theta")
+        _close(tr2["pk"][c], b["pk"], "pk")
+        tot += b["visits"]
+    assert np.array_equal(vis.astype(np.int64), tot)

@@ -73,3 +73,20 @@ def test_philox_population_statistics(amx):
     assert abs(x.mean() - 0.5) < 0.02 and abs(x.std() - 1.0) < 0.02
     assert 0.2 < r["sig"].std() / r["sig"].mean() < 1.0 or r["sig"].std() < 2.0
     assert len(np.unique(r["samples"][:, -1, 0])) > 200
+
+
+def test_host_callback_mode_against_oracle(amx, orc, ht):
+    """Stage 1 with the reference's scalar callback: the split kernels must reproduce the chain."""
+    wl = cases.workload("toy1")
+    ptr = ht.select(wl["target"])
+    init = cases.default_init(wl, 8)[1:3]
+    tape = cases.tape(555, cases.rwm_tape_len(2, 1000))
+    T = amx.Target(wl["target"], host_fn=ht.ptr)
+    r = amx.rwm_adapt(T, 1, 1000, 1, init, tapes=tape[None, :])
+    orc.tape(tape)
+    o = orc.rwm_within_model(1, 2, 1000, ptr, init)
+    rep_dev = np.all(r["samples"][0][1:] == r["samples"][0][:-1], axis=1)
+    rep_orc = np.all(o["samples"][1:] == o["samples"][:-1], axis=1)
+    assert np.array_equal(rep_dev, rep_orc)
+    assert _rel(r["samples"][0], o["samples"]) < 1e-9 and _rel(r["sig"][0], o["sig"]) < 1e-9
+    assert _rel(r["sig_trace"], o["sig_trace"]) < 1e-9
