@@ -162,6 +162,7 @@ def main():
     import torch.distributed as dist
 
     from automix_b200 import _lib as amx
+    from automix_b200 import shard
     from automix_b200 import workloads as W
 
     rank = int(os.environ.get("RANK", "0"))
@@ -188,7 +189,7 @@ def main():
     C, S = args.chains, args.sweeps
     nm = len(mix["dims"])
     pop = amx.RjPopulation(P, T, C, init, seed=20261018)
-    pop.set_chain_base(rank * C)
+    pop.set_chain_base(shard.weak_range(C, rank)[0])  # global chain ids: results independent of N
     pop.init_chains()
     pop.sweeps(1000, burning=True)  # burn-in: the chains forget the common start
     pop.collect(reset=True)
@@ -212,8 +213,7 @@ def main():
         pop.sweeps(S)
         ev[s][1].record(stream)
     pop.visits_to(hist.data_ptr())
-    if world > 1:
-        dist.all_reduce(hist)  # the one collective of the path: final model-visit histogram
+    shard.allreduce_sum_(hist)  # the one collective of the path: final model-visit histogram (NCCL)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clk = clocks.stop() if rank == 0 else None
@@ -221,16 +221,14 @@ def main():
     vis_local, st = pop.collect(reset=False)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     t_dev = torch.tensor([sum(step_ms) * 1e-3, t_wall], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    shard.allreduce_max_(t_dev)
     t_rj, t_rj_wall = (float(v) for v in t_dev.cpu())
     total_sweeps = float(world) * C * S * args.steps
     value = total_sweeps / t_rj
     hist_h = hist.cpu().numpy()
     assert int(hist_h.sum()) == int(total_sweeps), "model-visit histogram does not add up"
     flops = torch.tensor([float(st["flops"])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(flops)
+    shard.allreduce_sum_(flops)
     roof_rj = None
     if rank == 0:
         ach = float(st["flops"]) / (st["kernel_ms"] * 1e-3)  # this rank's dominant kernel, per-launch average
@@ -254,7 +252,7 @@ def main():
             P2 = amx.Proposal(mix)                       # H2D: proposal blob
             T2 = amx.Target(wl["target"])                # H2D: plug-in parameters
             pop2 = amx.RjPopulation(P2, T2, C, init_pin.numpy(), seed=7 + s)  # H2D: start vectors
-            pop2.set_chain_base(rank * C)
+            pop2.set_chain_base(shard.weak_range(C, rank)[0])
             pop2.init_chains()
             pop2.sweeps(S)
             v2, st2 = pop2.collect()                     # D2H: histogram + counters
@@ -263,8 +261,7 @@ def main():
             pop2.close(); T2.close(); P2.close()
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        shard.allreduce_max_(te)
         h2d = int(P.mix["wt"].nbytes + P.mix["mean"].nbytes + P.mix["tri"].nbytes + P.mix["sig"].nbytes + init.nbytes + 2048)
         e2e = {"value": float(world) * C * S * e2e_steps / float(te.cpu()[0]), "unit": "chain-sweeps/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
