@@ -37,7 +37,7 @@ namespace cg = cooperative_groups;
 
 namespace amx {
 
-constexpr int kEmThreads = 256;
+constexpr int kEmThreads = 128;
 constexpr int kEmWarps = kEmThreads / 32;
 constexpr int kEmLmax = AMX_MAX_COMPS;
 constexpr int kEmDmax = AMX_MAX_DIM;
@@ -66,6 +66,7 @@ struct EmCtrl {
   double cost, cost_prev, cost_best;
   double s2;
   double rec[kEmRecMax];  // family record of the component in progress (for solve_lower)
+  long long dbg[8];  // cycle counters (AMX_EM_DEBUG): data pass, arrive->leader, reduce, leader logic, wait, reload
   int best_L;
   double best_lam[kEmLmax];
   double best_mu[kEmLmax][kEmDmax];
@@ -74,9 +75,12 @@ struct EmCtrl {
 
 struct EmArgs {
   int d, Lmax, maxit;
+  int use_tma;  // 1: tile rows by cp.async.bulk + mbarrier; 0: coalesced per-thread loads into the tile
+  int nbuf;  // tile buffers per CTA: 2 = fetch of tile k+1 overlaps tile k, 1 = more resident CTAs
   long n, npad;
   const double *x;  // n x d row-major (device)
   double *xT, *E, *wnxt, *part;
+  unsigned *flags;  // [grid * 8] per-CTA release flags of the grid barrier
   EmCtrl *ctrl;
   const int *init_idx;  // device
   int *trace_L, *trace_ann;
@@ -104,17 +108,22 @@ __device__ __forceinline__ bool barrier_arrive(EmCtrl *ctrl, unsigned &epoch) {
   __syncthreads();
   return s_last != 0;
 }
-__device__ __forceinline__ void barrier_release(EmCtrl *ctrl, unsigned &epoch) {
+// Release: the leader's threads write one flag per CTA (32-byte stride: every waiter polls its own sector,
+// so there is no hot L2 line -- 592 CTAs polling one address saturate its slice and slow the leader down).
+__device__ __forceinline__ void barrier_release(unsigned *flags, unsigned &epoch) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicExch(&ctrl->gen, epoch + 1u);
-  }
+  __threadfence();
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) __stcg(flags + 8u * b, epoch + 1u);
   epoch++;
 }
-__device__ __forceinline__ void barrier_wait(EmCtrl *ctrl, unsigned &epoch) {
+__device__ __forceinline__ void barrier_wait(unsigned *flags, unsigned &epoch) {
   if (threadIdx.x == 0) {
-    while (ld_cg(&ctrl->gen) <= epoch) __nanosleep(40);
+    const unsigned *f = flags + 8u * blockIdx.x;
+    unsigned ns = 64;
+    while (ld_cg(f) <= epoch) {
+      __nanosleep(ns);
+      if (ns < 512) ns *= 2;
+    }
     __threadfence();
   }
   epoch++;
@@ -140,258 +149,490 @@ __device__ __forceinline__ void block_reduce_store(const double (&v)[NVAL], int 
   }
 }
 
-// leader: sum the per-CTA rows in CTA order into s_tot[0..nv)
-__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot) {
-  for (int q = threadIdx.x; q < nv; q += blockDim.x) {
-    double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; b++) t += ld_cg(part + (size_t)b * kEmNV + q);
-    s_tot[q] = t;
+// leader: sum the per-CTA partials into s_tot[0..nv).  Partials are stored value-major, part[q*grid + b], so
+// that the 32 lanes of a warp read 32 CONSECUTIVE CTAs of one value: one coalesced 256-byte request instead
+// of 32 scattered sectors (the scattered form kept one SM's L1TEX busy for ~60k cycles per pass at 592 CTAs).
+// Lane sums run over b = lane, lane+32, ... and are combined by a fixed shuffle tree, so the order of
+// additions depends only on the launch geometry (bitwise reproducible).  Two values are in flight per warp.
+__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot, double *s_chunk) {
+  (void)s_chunk;
+  const int G = (int)gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 2 * warp; q < nv; q += 2 * kEmWarps) {
+    const double *s0 = part + (size_t)q * G;
+    const bool two = (q + 1 < nv);
+    const double *s1 = part + (size_t)(two ? q + 1 : q) * G;
+    double t0 = 0.0, t1 = 0.0;
+    for (int base = 0; base < G; base += 32 * 20) {  // 20 x 2 independent loads in flight per lane
+      double v0[20], v1[20];
+#pragma unroll
+      for (int k = 0; k < 20; k++) {
+        const int b = base + lane + 32 * k;
+        v0[k] = (b < G) ? ld_cg(s0 + b) : 0.0;
+        v1[k] = (b < G) ? ld_cg(s1 + b) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 20; k++) {
+        t0 += v0[k];
+        t1 += v1[k];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+    }
+    if (lane == 0) {
+      s_tot[q] = t0;
+      if (two) s_tot[q + 1] = t1;
+    }
   }
   __syncthreads();
 }
 
-// ---- leader's scalar algorithm (thread 0 only) ------------------------------------------------------
-__device__ void em_renorm(EmCtrl *c) {
-  double s = 0.0;
-  for (int l = 0; l < c->L; l++) s += c->lam[l];
-  for (int l = 0; l < c->L; l++) c->lam[l] /= s;
-}
-// remove component `gone`, shifting the later ones down (:823-836, :908-921)
-__device__ void em_drop(EmCtrl *c, int d, int gone) {
-  const int tri = d * (d + 1) / 2;
-  for (int l = gone; l < c->L - 1; l++) {
-    c->lam[l] = c->lam[l + 1];
-    c->slot[l] = c->slot[l + 1];
-    for (int j = 0; j < d; j++) c->mu[l][j] = c->mu[l + 1][j];
-    for (int j = 0; j < tri; j++) c->B[l][j] = c->B[l + 1][j];
-  }
-  c->L--;
-}
-__device__ double em_cost(const EmCtrl *c, long n, int nparams) {  // :870-876
-  double s = 0.0;
-  for (int l = 0; l < c->L; l++) s += log((double)n * c->lam[l] / 12.0);
-  return (nparams / 2.0) * s + (c->L / 2.0) * log((double)n / 12.0) + c->L * (nparams + 1) / 2.0 - c->loglik;
-}
-// column-oriented in-place Cholesky on packed storage (:1682-1701)
-__device__ bool em_chol(int d, double *A) {
+// ---- the leader's section: the sequential CEM^2 logic, run by ALL threads of the last-arriving CTA ------
+// The hot part of the state is copied into shared memory; thread 0 takes the scalar decisions (sums in
+// the reference's index order), and everything with independent elements -- divisions, logarithms,
+// array shifts, copies, the rows of the Cholesky factor -- is spread over the CTA's threads.  Element-wise
+// arithmetic and its order are exactly those of the reference, so results do not depend on this split.
+enum EmAct { kActDone = 0, kActPlan, kActEndSweep, kActFinishIter };
+
+template <int DMAX>
+struct LeaderS {
+  int pass, L, c, next, forced_pending, natural, forced, iters, stop, status, best_L;
+  int act, keep, drop, savebest;
+  long comp_steps;
+  double flops, loglik, cost, cost_prev, cost_best, scal;
+  int slot[kEmLmax];
+  double lam[kEmLmax], colsum[kEmLmax], S1[kEmLmax], tmp[kEmLmax];
+  double Bc[DMAX * (DMAX + 1) / 2];
+  int chol_ok;
+};
+
+// in-place Cholesky of a packed d x d matrix in shared memory by one warp: lane r keeps row r in
+// registers, column pivots travel by shuffle (element arithmetic as automix.c:1686-1700)
+template <int DMAX>
+__device__ __forceinline__ bool warp_chol(double *Bs, int d) {
+  const int r = threadIdx.x & 31;
+  double row[DMAX];
+#pragma unroll
+  for (int j = 0; j < DMAX; j++) row[j] = (r < d && j <= r) ? Bs[AMX_TRI(r, j)] : 0.0;
   bool ok = true;
-  for (int cidx = 0; cidx < d; cidx++) {
-    double s = A[AMX_TRI(cidx, cidx)];
-    for (int j = 0; j < cidx; j++) s -= A[AMX_TRI(cidx, j)] * A[AMX_TRI(cidx, j)];
-    if (!(s > 0.0)) ok = false;
-    const double p = sqrt(s);
-    A[AMX_TRI(cidx, cidx)] = p;
-    for (int r = cidx + 1; r < d; r++) {
-      double t = A[AMX_TRI(r, cidx)];
-      for (int j = 0; j < cidx; j++) t -= A[AMX_TRI(r, j)] * A[AMX_TRI(cidx, j)];
-      A[AMX_TRI(r, cidx)] = t / p;
+#pragma unroll
+  for (int c = 0; c < DMAX; c++) {
+    if (c < d) {
+      double sp = row[c];
+#pragma unroll
+      for (int j = 0; j < c; j++) sp = fma(-row[j], row[j], sp);
+      const double spc = __shfl_sync(0xffffffffu, sp, c);
+      if (!(spc > 0.0)) ok = false;
+      const double p = sqrt(spc);
+      double t = row[c];
+#pragma unroll
+      for (int j = 0; j < c; j++) {
+        const double acj = __shfl_sync(0xffffffffu, row[j], c);
+        t = fma(-row[j], acj, t);
+      }
+      if (r > c) row[c] = t / p;
+      else if (r == c) row[c] = p;
     }
   }
+#pragma unroll
+  for (int j = 0; j < DMAX; j++)
+    if (r < d && j <= r) Bs[AMX_TRI(r, j)] = row[j];
   return ok;
 }
-// family record of component l for solve_lower (proposal flavour, include/amx_layout.h)
-__device__ void em_make_rec(EmCtrl *c, int d, int l) {
-  const int tri = d * (d + 1) / 2;
-  double prod = 1.0;
-  for (int i = 0; i < d; i++) prod *= c->B[l][AMX_TRI(i, i)];
-  double *r = c->rec;
-  r[0] = c->lam[l];
-  r[1] = 0.0;
-  r[2] = log(prod);
-  r[3] = -(d / 2.0) * log(2.0 * 3.14159265358979323846) - r[2];
-  for (int i = 0; i < d; i++) {
-    r[AMX_REC_HEAD + i] = c->mu[l][i];
-    r[AMX_REC_HEAD + d + i] = 1.0 / c->B[l][AMX_TRI(i, i)];
+
+// family record of component l (proposal flavour, include/amx_layout.h) from the factor in S.Bc
+template <int DMAX>
+__device__ __forceinline__ void leader_make_rec(EmCtrl *c, LeaderS<DMAX> &S, int d, int l) {
+  const int t = threadIdx.x, tri = d * (d + 1) / 2;
+  if (t == 0) {
+    double prod = 1.0;
+    for (int i = 0; i < d; i++) prod *= S.Bc[AMX_TRI(i, i)];
+    const double ld = log(prod);
+    c->rec[0] = S.lam[l];
+    c->rec[1] = 0.0;
+    c->rec[2] = ld;
+    c->rec[3] = -(d / 2.0) * log(2.0 * 3.14159265358979323846) - ld;
   }
-  for (int i = 0; i < tri; i++) r[AMX_REC_HEAD + 2 * d + i] = c->B[l][i];
+  if (t < d) {
+    c->rec[AMX_REC_HEAD + t] = ld_cg(&c->mu[l][t]);
+    c->rec[AMX_REC_HEAD + d + t] = 1.0 / S.Bc[AMX_TRI(t, t)];
+  }
+  for (int q = t; q < tri; q += blockDim.x) c->rec[AMX_REC_HEAD + 2 * d + q] = S.Bc[q];
 }
 
-// start the update of component c->c from the current column sums and first moment (:773-801)
-__device__ void em_plan_step(EmCtrl *c, const EmArgs &a) {
-  const int d = a.d, nparams = d + d * (d + 1) / 2;
-  for (;;) {
-    const int cc = c->c;
-    double tot = 0.0, wkeep = 0.0;
-    for (int l = 0; l < c->L; l++) {
-      const double wl = max_m(0.0, (c->colsum[l] - nparams / 2.0));
-      if (l == cc) wkeep = wl;
-      tot += wl;
+// remove component `gone` (:823-836, :908-921): thread q moves element q of every later component
+template <int DMAX>
+__device__ __forceinline__ void leader_drop(EmCtrl *c, LeaderS<DMAX> &S, int d, int gone) {
+  const int t = threadIdx.x, tri = d * (d + 1) / 2, L = S.L;
+  for (int q = t; q < tri; q += blockDim.x)
+    for (int l = gone; l < L - 1; l++) c->B[l][q] = ld_cg(&c->B[l + 1][q]);
+  if (t < d)
+    for (int l = gone; l < L - 1; l++) c->mu[l][t] = ld_cg(&c->mu[l + 1][t]);
+  __syncthreads();
+  if (t == 0) {
+    for (int l = gone; l < L - 1; l++) {
+      S.lam[l] = S.lam[l + 1];
+      S.slot[l] = S.slot[l + 1];
     }
-    c->lam[cc] = wkeep / tot;
-    em_renorm(c);
-    c->comp_steps++;
-    c->flops += (double)a.n * (2.0 * d * d + 8.0 * d + 4.0 * c->L + 7.0);
-    if (c->lam[cc] > 0.005) {
-      for (int j = 0; j < d; j++) {
-        c->mu[cc][j] = c->S1[j] / c->colsum[cc];
-        c->rec[AMX_REC_HEAD + j] = c->mu[cc][j];  // the scatter pass centres on the NEW mean (:803-809)
-      }
-      c->pass = kPassScatter;
-      return;
-    }
-    // natural annihilation (:821-845); the responsibilities must be refreshed before the
-    // next component can be looked at
-    c->natural = 1;
-    em_drop(c, d, cc);
-    em_renorm(c);
-    c->next = (cc < c->L) ? cc : 0;
-    c->pass = kPassRefresh;
-    return;
+    S.L = L - 1;
   }
+  __syncthreads();
 }
 
-__device__ void em_finish_iteration(EmCtrl *c, const EmArgs &a) {
-  if (c->iters > a.maxit) c->stop = 1;  // :961-963
-  c->cost_prev = c->cost;
-  const int t = c->iters - 1;
-  if (a.trace_ann) a.trace_ann[t] = c->natural + c->forced;
-  if (a.trace_cost) a.trace_cost[t] = c->cost;
-  if (a.trace_loglik) a.trace_loglik[t] = c->loglik;
-  if (a.trace_L) a.trace_L[t] = c->L;
-  if (c->stop) {
-    c->pass = kPassStop;
-    return;
+// lam /= sum(lam): the sum in index order by thread 0, the divisions in parallel
+template <int DMAX>
+__device__ __forceinline__ void leader_renorm(LeaderS<DMAX> &S) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    double sum = 0.0;
+    for (int l = 0; l < S.L; l++) sum += S.lam[l];
+    S.scal = sum;
   }
-  c->iters++;
-  c->natural = c->forced = 0;
-  c->c = 0;
-  em_plan_step(c, a);
+  __syncthreads();
+  if (t < S.L) S.lam[t] /= S.scal;
+  __syncthreads();
 }
 
-__device__ void em_end_of_sweep(EmCtrl *c, const EmArgs &a) {
-  const int d = a.d, nparams = d + d * (d + 1) / 2, tri = d * (d + 1) / 2;
-  c->cost = em_cost(c, a.n, nparams);
-  if (c->iters == 1) c->cost_prev = c->cost;
-  if (c->iters == 1 || c->cost < c->cost_best) {  // :881-893
-    c->best_L = c->L;
-    c->cost_best = c->cost;
-    for (int l = 0; l < c->L; l++) {
-      c->best_lam[l] = c->lam[l];
-      for (int j = 0; j < d; j++) c->best_mu[l][j] = c->mu[l][j];
-      for (int j = 0; j < tri; j++) c->best_B[l][j] = c->B[l][j];
-    }
+// MML cost (:870-876): logarithms in parallel, their sum in index order
+template <int DMAX>
+__device__ __forceinline__ void leader_cost(LeaderS<DMAX> &S, long n, int nparams) {
+  const int t = threadIdx.x;
+  if (t < S.L) S.tmp[t] = log((double)n * S.lam[t] / 12.0);
+  __syncthreads();
+  if (t == 0) {
+    double sum = 0.0;
+    for (int l = 0; l < S.L; l++) sum += S.tmp[l];
+    S.cost = (nparams / 2.0) * sum + (S.L / 2.0) * log((double)n / 12.0) + S.L * (nparams + 1) / 2.0 - S.loglik;
   }
-  if (fabs(c->cost_prev - c->cost) < min_m(1E-5 * fabs(c->cost_prev), 0.01) && c->iters > 1) {  // :894
-    if (c->L == 1) {
-      c->stop = 1;
-    } else {
-      c->forced = 2;
-      double lo = c->lam[0];
-      int gone = 0;
-      for (int l = 1; l < c->L; l++)
-        if (lo > c->lam[l]) {
-          lo = c->lam[l];
-          gone = l;
-        }
-      em_drop(c, d, gone);
-      em_renorm(c);
-      c->forced_pending = 1;
-      c->next = 0;
-      c->pass = kPassRefresh;
-      return;
-    }
-  }
-  em_finish_iteration(c, a);
+  __syncthreads();
 }
 
-// leader after a pass: s_tot holds the reduced partial row
-__device__ void em_leader(EmCtrl *c, const EmArgs &a, int pass, const double *s_tot) {
-  const int d = a.d, tri = d * (d + 1) / 2;
+template <int DMAX>
+__device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const double *s_tot, LeaderS<DMAX> &S) {
+  const int t = threadIdx.x, d = a.d, tri = d * (d + 1) / 2, nparams = d + tri;
+  // ---- load the hot state
+  if (t == 0) {
+    S.pass = ld_cg(&c->pass); S.L = ld_cg(&c->L); S.c = ld_cg(&c->c); S.next = ld_cg(&c->next);
+    S.forced_pending = ld_cg(&c->forced_pending); S.natural = ld_cg(&c->natural); S.forced = ld_cg(&c->forced);
+    S.iters = ld_cg(&c->iters); S.stop = ld_cg(&c->stop); S.status = ld_cg(&c->status); S.best_L = ld_cg(&c->best_L);
+    S.comp_steps = ld_cg(&c->comp_steps); S.flops = ld_cg(&c->flops); S.loglik = ld_cg(&c->loglik);
+    S.cost = ld_cg(&c->cost); S.cost_prev = ld_cg(&c->cost_prev); S.cost_best = ld_cg(&c->cost_best);
+    S.act = kActDone; S.keep = 0; S.drop = -1; S.savebest = 0; S.chol_ok = 1;
+  }
+  if (t < kEmLmax) {
+    S.slot[t] = ld_cg(&c->slot[t]);
+    S.lam[t] = ld_cg(&c->lam[t]);
+    S.colsum[t] = ld_cg(&c->colsum[t]);
+    S.S1[t] = ld_cg(&c->S1[t]);
+  }
+  __syncthreads();
+
   if (pass == kPassInitStats) {
     // :700-723 common isotropic start; s_tot = [sum x_j (d) | sum x_j^2 (d)]
-    double s2 = 0.0;
-    const double len = (double)a.n;
-    for (int j = 0; j < d; j++) s2 += (s_tot[d + j] - s_tot[j] * s_tot[j] / len) / len;
-    s2 /= (10.0 * d);
-    c->s2 = s2;
-    c->L = a.Lmax;
-    for (int l = 0; l < c->L; l++) {
-      c->slot[l] = l;
-      c->lam[l] = 1.0 / c->L;
-      for (int j = 0; j < d; j++) c->mu[l][j] = a.x[(size_t)a.init_idx[l] * d + j];
-      for (int j = 0; j < tri; j++) c->B[l][j] = 0.0;
-      for (int j = 0; j < d; j++) c->B[l][AMX_TRI(j, j)] = s2;
-      if (!em_chol(d, c->B[l])) c->status = AMX_ENUMERIC;
+    if (t == 0) {
+      double s2 = 0.0;
+      const double len = (double)a.n;
+      for (int j = 0; j < d; j++) s2 += (s_tot[d + j] - s_tot[j] * s_tot[j] / len) / len;
+      s2 /= (10.0 * d);
+      c->s2 = s2;
+      S.scal = sqrt(s2);  // chol of s2 * I (:716-721): sqrt on the diagonal, zeros below
+      if (!(s2 > 0.0)) S.status = AMX_ENUMERIC;
+      S.L = a.Lmax;
+      S.c = 0;
+      S.pass = kPassInitDens;
     }
-    c->c = 0;
-    em_make_rec(c, d, 0);
-    c->pass = kPassInitDens;
-    return;
-  }
-  if (pass == kPassInitDens) {  // one component's start densities are in place
-    c->c++;
-    if (c->c < c->L) {
-      em_make_rec(c, d, c->c);
-      c->pass = kPassInitDens;
-    } else {
-      c->next = 0;
-      c->iters = 0;  // the refresh that follows is the initial E-step (:733-744)
-      c->pass = kPassRefresh;
+    __syncthreads();
+    for (int q = t; q < a.Lmax * d; q += blockDim.x) {
+      const int l = q / d, j = q % d;
+      c->mu[l][j] = a.x[(size_t)a.init_idx[l] * d + j];
     }
-    return;
-  }
-  if (pass == kPassScatter) {
+    for (int q = t; q < a.Lmax * tri; q += blockDim.x) c->B[q / tri][q % tri] = 0.0;
+    __syncthreads();
+    for (int q = t; q < a.Lmax * d; q += blockDim.x) c->B[q / d][AMX_TRI(q % d, q % d)] = S.scal;
+    if (t < a.Lmax) {
+      S.slot[t] = t;
+      S.lam[t] = 1.0 / a.Lmax;
+    }
+    for (int q = t; q < tri; q += blockDim.x) S.Bc[q] = 0.0;
+    __syncthreads();
+    if (t < d) S.Bc[AMX_TRI(t, t)] = S.scal;
+    __syncthreads();
+    leader_make_rec<DMAX>(c, S, d, 0);
+  } else if (pass == kPassInitDens) {  // one component's start densities are in place
+    if (t == 0) {
+      S.c++;
+      if (S.c < S.L) {
+        S.pass = kPassInitDens;
+      } else {
+        S.next = 0;
+        S.iters = 0;  // the refresh that follows is the initial E-step (:733-744)
+        S.pass = kPassRefresh;
+      }
+    }
+    for (int q = t; q < tri; q += blockDim.x) S.Bc[q] = ld_cg(&c->B[0][q]);  // all start factors are equal
+    __syncthreads();
+    if (S.c < S.L) leader_make_rec<DMAX>(c, S, d, S.c);
+  } else if (pass == kPassScatter) {
     // :803-813 centred scatter / sum of weights, then Cholesky
-    const int cc = c->c;
-    for (int j = 0; j < tri; j++) c->B[cc][j] = s_tot[j] / c->colsum[cc];
-    if (!em_chol(d, c->B[cc])) {
-      c->status = AMX_ENUMERIC;
-      c->stop = 1;
-      c->pass = kPassStop;
-      return;
+    const int cc = S.c;
+    for (int q = t; q < tri; q += blockDim.x) S.Bc[q] = s_tot[q] / S.colsum[cc];
+    __syncthreads();
+    if (t < 32) {
+      const bool ok = warp_chol<DMAX>(S.Bc, d);
+      if (t == 0) S.chol_ok = ok ? 1 : 0;
     }
-    em_make_rec(c, d, cc);
-    c->next = (cc + 1 < c->L) ? cc + 1 : 0;
-    c->pass = kPassDensRefresh;
-    return;
+    __syncthreads();
+    for (int q = t; q < tri; q += blockDim.x) c->B[cc][q] = S.Bc[q];
+    leader_make_rec<DMAX>(c, S, d, cc);
+    if (t == 0) {
+      if (!S.chol_ok) {
+        S.status = AMX_ENUMERIC;
+        S.stop = 1;
+        S.pass = kPassStop;
+      } else {
+        S.next = (cc + 1 < S.L) ? cc + 1 : 0;
+        S.pass = kPassDensRefresh;
+      }
+    }
+  } else {
+    // a refresh finished: s_tot = [colsum (Lmax) | loglik | fallbacks | S1 (d)]
+    if (t < S.L) S.colsum[t] = s_tot[t];
+    if (t < d) S.S1[t] = s_tot[kEmLmax + 2 + t];
+    if (t == 0) {
+      S.loglik = s_tot[kEmLmax] - 500.0 * s_tot[kEmLmax + 1];
+      if (S.iters == 0) {  // initial E-step done: start outer iteration 1
+        S.iters = 1;
+        S.natural = S.forced = 0;
+        S.c = 0;
+        S.act = kActPlan;
+      } else if (S.forced_pending) {  // refresh after a forced annihilation (:931-958)
+        S.act = kActFinishIter;
+      } else {
+        if (pass == kPassDensRefresh) S.c++;  // component kept: move on (:819)
+        S.act = (S.c < S.L) ? kActPlan : kActEndSweep;
+      }
+    }
+    __syncthreads();
+    if (S.forced_pending) {  // uniform: the cost after the forced annihilation
+      leader_cost<DMAX>(S, a.n, nparams);
+      if (t == 0) S.forced_pending = 0;
+      __syncthreads();
+    }
+    while (S.act != kActDone) {
+      const int act = S.act;
+      __syncthreads();
+      if (act == kActPlan) {
+        // start the update of component S.c from the column sums and the first moment (:773-801)
+        const int cc = S.c;
+        if (t == 0) {
+          double tot = 0.0, wkeep = 0.0;
+          for (int l = 0; l < S.L; l++) {
+            const double wl = max_m(0.0, (S.colsum[l] - nparams / 2.0));
+            if (l == cc) wkeep = wl;
+            tot += wl;
+          }
+          S.lam[cc] = wkeep / tot;
+          S.comp_steps++;
+          S.flops += (double)a.n * (2.0 * d * d + 8.0 * d + 4.0 * S.L + 7.0);
+        }
+        __syncthreads();
+        leader_renorm<DMAX>(S);
+        if (S.lam[cc] > 0.005) {  // uniform branch (shared value)
+          if (t < d) {
+            const double m = S.S1[t] / S.colsum[cc];
+            c->mu[cc][t] = m;
+            c->rec[AMX_REC_HEAD + t] = m;  // the scatter pass centres on the NEW mean (:803-809)
+          }
+          if (t == 0) {
+            S.pass = kPassScatter;
+            S.act = kActDone;
+          }
+        } else {  // natural annihilation (:821-845): refresh before the next component is looked at
+          leader_drop<DMAX>(c, S, d, cc);
+          leader_renorm<DMAX>(S);
+          if (t == 0) {
+            S.natural = 1;
+            S.next = (cc < S.L) ? cc : 0;
+            S.pass = kPassRefresh;
+            S.act = kActDone;
+          }
+        }
+      } else if (act == kActEndSweep) {
+        leader_cost<DMAX>(S, a.n, nparams);
+        if (t == 0) {
+          if (S.iters == 1) S.cost_prev = S.cost;
+          S.savebest = (S.iters == 1 || S.cost < S.cost_best) ? 1 : 0;  // :881-893
+          if (S.savebest) {
+            S.best_L = S.L;
+            S.cost_best = S.cost;
+          }
+          S.drop = -1;
+          if (fabs(S.cost_prev - S.cost) < min_m(1E-5 * fabs(S.cost_prev), 0.01) && S.iters > 1) {  // :894
+            if (S.L == 1) {
+              S.stop = 1;
+            } else {
+              S.forced = 2;
+              double lo = S.lam[0];
+              int gone = 0;
+              for (int l = 1; l < S.L; l++)
+                if (lo > S.lam[l]) {
+                  lo = S.lam[l];
+                  gone = l;
+                }
+              S.drop = gone;
+            }
+          }
+        }
+        __syncthreads();
+        if (S.savebest) {
+          if (t < S.L) c->best_lam[t] = S.lam[t];
+          for (int q = t; q < S.L * d; q += blockDim.x) c->best_mu[q / d][q % d] = ld_cg(&c->mu[q / d][q % d]);
+          for (int q = t; q < S.L * tri; q += blockDim.x) c->best_B[q / tri][q % tri] = ld_cg(&c->B[q / tri][q % tri]);
+          __syncthreads();
+        }
+        if (S.drop >= 0) {
+          leader_drop<DMAX>(c, S, d, S.drop);
+          leader_renorm<DMAX>(S);
+          if (t == 0) {
+            S.forced_pending = 1;
+            S.next = 0;
+            S.pass = kPassRefresh;
+            S.act = kActDone;
+          }
+        } else if (t == 0) {
+          S.act = kActFinishIter;
+        }
+      } else {  // kActFinishIter (:961-970)
+        if (t == 0) {
+          if (S.iters > a.maxit) S.stop = 1;
+          S.cost_prev = S.cost;
+          const int it = S.iters - 1;
+          if (a.trace_ann) a.trace_ann[it] = S.natural + S.forced;
+          if (a.trace_cost) a.trace_cost[it] = S.cost;
+          if (a.trace_loglik) a.trace_loglik[it] = S.loglik;
+          if (a.trace_L) a.trace_L[it] = S.L;
+          if (S.stop) {
+            S.pass = kPassStop;
+            S.act = kActDone;
+          } else {
+            S.iters++;
+            S.natural = S.forced = 0;
+            S.c = 0;
+            S.act = kActPlan;
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
-  // a refresh finished: s_tot = [colsum (L) | loglik | fallbacks | S1 (d)]
-  for (int l = 0; l < c->L; l++) c->colsum[l] = s_tot[l];
-  c->loglik = s_tot[kEmLmax] - 500.0 * s_tot[kEmLmax + 1];
-  for (int j = 0; j < d; j++) c->S1[j] = s_tot[kEmLmax + 2 + j];
-  if (c->iters == 0) {  // initial E-step done: start outer iteration 1
-    c->iters = 1;
-    c->natural = c->forced = 0;
-    c->c = 0;
-    em_plan_step(c, a);
-    return;
+  __syncthreads();
+  // ---- store the hot state
+  if (t == 0) {
+    c->pass = S.pass; c->L = S.L; c->c = S.c; c->next = S.next; c->forced_pending = S.forced_pending;
+    c->natural = S.natural; c->forced = S.forced; c->iters = S.iters; c->stop = S.stop; c->status = S.status;
+    c->best_L = S.best_L; c->comp_steps = S.comp_steps; c->flops = S.flops; c->loglik = S.loglik;
+    c->cost = S.cost; c->cost_prev = S.cost_prev; c->cost_best = S.cost_best;
   }
-  if (c->forced_pending) {  // refresh after a forced annihilation (:931-958)
-    c->forced_pending = 0;
-    const int nparams = d + d * (d + 1) / 2;
-    c->cost = em_cost(c, a.n, nparams);
-    em_finish_iteration(c, a);
-    return;
+  if (t < kEmLmax) {
+    c->slot[t] = S.slot[t];
+    c->lam[t] = S.lam[t];
+    c->colsum[t] = S.colsum[t];
+    c->S1[t] = S.S1[t];
   }
-  if (pass == kPassDensRefresh) c->c++;  // component kept: move on (:819)
-  if (c->c < c->L) em_plan_step(c, a);
-  else em_end_of_sweep(c, a);
+}
+
+// ---- TMA (bulk asynchronous copy) + mbarrier -----------------------------------------------------------
+// A tile row (128 consecutive samples of one SoA array = 1 KB) is fetched by one cp.async.bulk issued by
+// one thread; completion is counted in bytes on an mbarrier in shared memory.  No registers are staged
+// and the fetch overlaps the other resident CTAs' arithmetic.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_row(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kEmTS = kEmThreads + 4;  // tile row stride in doubles: spreads the column reduction over the banks
+
+// accumulate rows [R0, R1) of the packed lower triangle of w dx dx^T into acc[0 .. N)
+template <int DMAX, int R0, int R1, int NACC>
+__device__ __forceinline__ void scatter_rows(double (&acc)[NACC], const double *xs, const double *mu, double w, int tt,
+                                             int d) {
+  double dx[DMAX];
+#pragma unroll
+  for (int j = 0; j < DMAX; j++) dx[j] = (j < d) ? xs[j * kEmTS + tt] - mu[j] : 0.0;
+  int q = 0;
+#pragma unroll
+  for (int j = R0; j < R1; j++) {
+    const double wd = w * dx[j];
+#pragma unroll
+    for (int k = 0; k <= j; k++, q++) acc[q] = fma(wd, dx[k], acc[q]);
+  }
 }
 
 // ---- the fit kernel -------------------------------------------------------------------------------------
+// 128 threads per CTA, one tile = 128 samples.  Shared-memory tile rows (stride kEmTS doubles):
+//   xs[d]  sample coordinates     Es[Lmax]  density cache rows of the live components (component order)
+//   ws[1]  responsibilities of the "next" component
 template <int DMAX>
-__global__ void __launch_bounds__(kEmThreads) em_fit_kernel(EmArgs a) {
+__global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
   constexpr int TRI = DMAX * (DMAX + 1) / 2;
-  constexpr int NVC = kEmLmax + 2 + DMAX;       // refresh partial row
-  constexpr int NVMAX = TRI > NVC ? TRI : NVC;  // scatter partial row is TRI
-  __shared__ double s_red[kEmWarps * NVMAX];
-  __shared__ double s_tot[kEmNV];
+  constexpr int NRED = TRI > 2 * DMAX ? TRI : 2 * DMAX;
+  constexpr int RSPLIT = DMAX > 8 ? 8 : DMAX;  // DMAX > 8: two row groups, [0,8) and [8,DMAX)
+  extern __shared__ __align__(16) double tile[];
+  __shared__ __align__(8) uint64_t s_bar[4];  // one mbarrier per tile buffer / pipeline stage
+  __shared__ double s_red[kEmWarps * NRED];
+  __shared__ double s_tot[NRED > kEmLmax + 2 + DMAX ? NRED : kEmLmax + 2 + DMAX];
+  __shared__ double s_chunk[8 * (NRED > kEmLmax + 2 + DMAX ? NRED : kEmLmax + 2 + DMAX)];
   __shared__ double s_rec[AMX_REC_HEAD + 2 * DMAX + TRI];
   __shared__ double s_lam[kEmLmax];
   __shared__ int s_slot[kEmLmax];
   __shared__ int s_pass, s_L, s_c, s_next;
+  __shared__ LeaderS<DMAX> s_lead;
 
   EmCtrl *ctrl = a.ctrl;
   const int d = a.d;
   const long n = a.n, np = a.npad;
+  const long ntiles = np / kEmThreads;
   const long stride = (long)gridDim.x * blockDim.x;
   const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  double *part_row = a.part + (size_t)blockIdx.x * kEmNV;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int tile_doubles = (d + a.Lmax + 1) * kEmTS;  // two such buffers: fetch of tile k+1 overlaps tile k
+  double *part_col = a.part + blockIdx.x;  // value q of this CTA lives at part_col[q * gridDim.x]
+  const size_t pstride = gridDim.x;
   unsigned epoch = 0;
+  uint32_t tma_phase[4] = {0u, 0u, 0u, 0u};
   int pass = kPassInitStats;
+  if (t == 0) {
+    for (int q = 0; q < 4; q++) mbar_init(&s_bar[q], 1);
+  }
+  __syncthreads();
 
   for (;;) {
     // ------------------------------------------------------------------ the data pass
+    const long long tk0 = clock64();
     int nv = 0;
     if (pass == kPassInitStats) {
       // transpose x -> xT and accumulate sum x_j, sum x_j^2 (:700-711)
@@ -408,111 +649,310 @@ __global__ void __launch_bounds__(kEmThreads) em_fit_kernel(EmArgs a) {
             v[DMAX + j] = fma(xv, xv, v[DMAX + j]);
           }
       }
-      // pack as [sum (d) | sumsq (d)]
-      double w[2 * DMAX];
+      // warp -> CTA reduction, packed as [sum (d) | sumsq (d)]
 #pragma unroll
-      for (int j = 0; j < 2 * DMAX; j++) w[j] = 0.0;
-#pragma unroll
-      for (int j = 0; j < DMAX; j++)
-        if (j < d) {
-          aset(w, j, v[j]);
-          aset(w, d + j, v[DMAX + j]);
-        }
+      for (int j = 0; j < 2 * DMAX; j++) {
+        const double r = warp_sum(v[j]);
+        if (lane == 0) s_red[warp * NRED + j] = r;
+      }
+      __syncthreads();
+      if (t < 2 * d) {
+        const int src = t < d ? t : DMAX + (t - d);
+        double tot = 0.0;
+        for (int w = 0; w < kEmWarps; w++) tot += s_red[w * NRED + src];
+        part_col[(size_t)t * pstride] = tot;
+      }
       nv = 2 * d;
-      block_reduce_store<2 * DMAX>(w, nv, s_red, part_row);
     } else if (pass == kPassInitDens) {
       const int slot = s_slot[s_c];
       for (long i = i0; i < n; i += stride) {
         double xv[DMAX], r[DMAX];
 #pragma unroll
         for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? __ldcg(a.xT + (size_t)j * np + i) : 0.0;
-        const double lpd = fma(-0.5, solve_lower<DMAX>(s_rec, d, xv, r), s_rec[3]);
+        const double lpd = fma(-0.5, solve_lower<DMAX, true>(s_rec, d, xv, r), s_rec[3]);
         __stcg(a.E + (size_t)slot * np + i, exp(lpd));
       }
       nv = 0;
     } else if (pass == kPassScatter) {
-      double acc[TRI];
+      // ---- S2 = sum_i wnxt_i (x_i - mu)(x_i - mu)^T, rows split over two thread groups when DMAX > 8
+      constexpr int NLO = RSPLIT * (RSPLIT + 1) / 2, NHI = TRI - NLO;
+      constexpr int NACC = NLO > NHI ? NLO : NHI;
+      double acc[NACC];  // one row group per thread: [0,RSPLIT) for threads 0..63, [RSPLIT,DMAX) for 64..127
 #pragma unroll
-      for (int q = 0; q < TRI; q++) acc[q] = 0.0;
+      for (int q = 0; q < NACC; q++) acc[q] = 0.0;
       const double *mu = s_rec + AMX_REC_HEAD;
-      for (long i = i0; i < n; i += stride) {
-        const double w = __ldcg(a.wnxt + i);
-        double dx[DMAX];
+      // The scatter pass needs only d+1 rows per tile, so the tile memory holds NST of them: a NST-deep
+      // TMA pipeline that keeps NST-1 fetches in flight per CTA and hides the HBM latency.
+      const int stage_doubles = (d + 1) * kEmTS;
+      int NST = (a.nbuf * tile_doubles) / stage_doubles;
+      NST = NST > 4 ? 4 : NST;
+      auto fetch = [&](long tl, int st) {  // warp 0: one bulk copy per tile row, lanes in parallel
+        double *xs = tile + st * stage_doubles;
+        fence_proxy_async();
+        if (lane == 0) mbar_expect_tx(&s_bar[st], (uint32_t)((d + 1) * kEmThreads * 8));
+        __syncwarp();
+        for (int j = lane; j <= d; j += 32)
+          tma_load_row(xs + j * kEmTS, (j < d ? a.xT + (size_t)j * np : a.wnxt) + tl * kEmThreads, kEmThreads * 8,
+                       &s_bar[st]);
+      };
+      if (!a.use_tma) {
+        // coalesced loads: thread t reads sample tl*128+t of every row (one 1 KB request per warp-row);
+        // with DMAX > 8 the two row groups each read samples tt and tt+64
+        for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+          const long i = tl * kEmThreads;
+          if constexpr (DMAX <= 8) {
+            double dx[DMAX];
 #pragma unroll
-        for (int j = 0; j < DMAX; j++) dx[j] = (j < d) ? __ldcg(a.xT + (size_t)j * np + i) - mu[j] : 0.0;
+            for (int j = 0; j < DMAX; j++) dx[j] = (j < d) ? __ldcg(a.xT + (size_t)j * np + i + t) - mu[j] : 0.0;
+            const double w = __ldcg(a.wnxt + i + t);
+            int q = 0;
 #pragma unroll
-        for (int j = 0; j < DMAX; j++) {
-          const double wd = w * dx[j];
+            for (int j = 0; j < DMAX; j++) {
+              const double wd = w * dx[j];
 #pragma unroll
-          for (int k = 0; k <= j; k++) acc[AMX_TRI(j, k)] = fma(wd, dx[k], acc[AMX_TRI(j, k)]);
+              for (int k = 0; k <= j; k++, q++) acc[q] = fma(wd, dx[k], acc[q]);
+            }
+          } else {
+            const int tt = t & 63;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const long ii = i + tt + 64 * h;
+              double dx[DMAX];
+#pragma unroll
+              for (int j = 0; j < DMAX; j++) dx[j] = (j < d) ? __ldcg(a.xT + (size_t)j * np + ii) - mu[j] : 0.0;
+              const double w = __ldcg(a.wnxt + ii);
+              int q = 0;
+              if (t < 64) {
+#pragma unroll
+                for (int j = 0; j < RSPLIT; j++) {
+                  const double wd = w * dx[j];
+#pragma unroll
+                  for (int k = 0; k <= j; k++, q++) acc[q] = fma(wd, dx[k], acc[q]);
+                }
+              } else {
+#pragma unroll
+                for (int j = RSPLIT; j < DMAX; j++) {
+                  const double wd = w * dx[j];
+#pragma unroll
+                  for (int k = 0; k <= j; k++, q++) acc[q] = fma(wd, dx[k], acc[q]);
+                }
+              }
+            }
+          }
         }
       }
-      nv = d * (d + 1) / 2;  // rows j<d of the packed triangle are exactly the first tri(d) entries
-      block_reduce_store<TRI>(acc, nv, s_red, part_row);
+      if (a.use_tma && warp == 0)
+        for (int q = 0; q < NST - 1; q++)
+          if ((long)blockIdx.x + (long)q * gridDim.x < ntiles) fetch(blockIdx.x + (long)q * gridDim.x, q);
+      int st = 0;
+      for (long tl = blockIdx.x; a.use_tma && tl < ntiles; tl += gridDim.x) {
+        const long ahead = tl + (long)(NST - 1) * gridDim.x;
+        if (warp == 0 && ahead < ntiles) fetch(ahead, (st + NST - 1) % NST);  // that stage was drained last iteration
+        mbar_wait(&s_bar[st], tma_phase[st]);
+        tma_phase[st] ^= 1u;
+        const double *xs = tile + st * stage_doubles, *ws = xs + d * kEmTS;
+        if constexpr (DMAX <= 8) {
+          scatter_rows<DMAX, 0, DMAX>(acc, xs, mu, ws[t], t, d);  // padding samples carry w = 0
+        } else {
+          const int tt = t & 63;
+          if (t < 64) {
+            scatter_rows<DMAX, 0, RSPLIT>(acc, xs, mu, ws[tt], tt, d);
+            scatter_rows<DMAX, 0, RSPLIT>(acc, xs, mu, ws[tt + 64], tt + 64, d);
+          } else {
+            scatter_rows<DMAX, RSPLIT, DMAX>(acc, xs, mu, ws[tt], tt, d);
+            scatter_rows<DMAX, RSPLIT, DMAX>(acc, xs, mu, ws[tt + 64], tt + 64, d);
+          }
+        }
+        __syncthreads();  // everyone is done with this stage before it is refilled
+        st = (st + 1 == NST) ? 0 : st + 1;
+      }
+      // warps 0,1 hold rows [0,RSPLIT) at s_red[..][q]; warps 2,3 hold the rest at s_red[..][NLO + q]
+#pragma unroll
+      for (int q = 0; q < NACC; q++) {
+        const double r = warp_sum(acc[q]);
+        const int dst = (DMAX <= 8 || warp < 2) ? q : NLO + q;
+        if (lane == 0 && dst < NRED) s_red[warp * NRED + dst] = r;
+      }
+      __syncthreads();
+      nv = d * (d + 1) / 2;  // rows j<d of the packed triangle are its first tri(d) entries
+      for (int q = t; q < nv; q += blockDim.x) {
+        double tot = 0.0;
+        if (DMAX <= 8) {
+          for (int w = 0; w < kEmWarps; w++) tot += s_red[w * NRED + q];
+        } else if (q < NLO) {
+          tot = s_red[0 * NRED + q] + s_red[1 * NRED + q];
+        } else {
+          tot = s_red[2 * NRED + q] + s_red[3 * NRED + q];
+        }
+        part_col[(size_t)q * pstride] = tot;
+      }
     } else if (pass == kPassDensRefresh || pass == kPassRefresh) {
+      // ---- (new density column,) responsibilities, column sums, log-likelihood, next first moment
       const int L = s_L, nx = s_next, cc = s_c;
       const bool dens = (pass == kPassDensRefresh);
       const int cslot = dens ? s_slot[cc] : 0;
-      double v[NVC];
-#pragma unroll
-      for (int q = 0; q < NVC; q++) v[q] = 0.0;
-      for (long i = i0; i < n; i += stride) {
-        double xv[DMAX];
-#pragma unroll
-        for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? __ldcg(a.xT + (size_t)j * np + i) : 0.0;
-        double enew = 0.0;
-        if (dens) {
-          double r[DMAX];
-          enew = exp(fma(-0.5, solve_lower<DMAX>(s_rec, d, xv, r), s_rec[3]));
-          __stcg(a.E + (size_t)cslot * np + i, enew);
-        }
-        double t[kEmLmax];
-        double s = 0.0;
-#pragma unroll
-        for (int l = 0; l < kEmLmax; l++) {
-          if (l < L) {
-            const double e = (dens && l == cc) ? enew : __ldcg(a.E + (size_t)s_slot[l] * np + i);
-            t[l] = s_lam[l] * e;
-            s += t[l];
+      const int col = t >> 2, prt = t & 3;  // reduction role: 32 columns x 4 partial sums
+      double acc_col = 0.0, acc_s1 = 0.0, ll = 0.0, nfb = 0.0;
+      auto fetch = [&](long tl, int bf) {  // warp 0: one bulk copy per tile row, lanes in parallel
+        double *xs = tile + bf * tile_doubles, *Es = xs + d * kEmTS;
+        fence_proxy_async();
+        const int rows = d + L - (dens ? 1 : 0);
+        if (lane == 0) mbar_expect_tx(&s_bar[bf], (uint32_t)(rows * kEmThreads * 8));
+        __syncwarp();
+        for (int q = lane; q < d + L; q += 32) {
+          if (q < d) {
+            tma_load_row(xs + q * kEmTS, a.xT + (size_t)q * np + tl * kEmThreads, kEmThreads * 8, &s_bar[bf]);
+          } else {
+            const int l = q - d;
+            if (!(dens && l == cc))
+              tma_load_row(Es + l * kEmTS, a.E + (size_t)s_slot[l] * np + tl * kEmThreads, kEmThreads * 8, &s_bar[bf]);
           }
         }
-        double wn;
-        if (s > 0) {  // the reference's guard (:855-866)
-          const double inv = 1.0 / s;
-          v[kEmLmax] += log(s);
-          wn = 0.0;
-#pragma unroll
-          for (int l = 0; l < kEmLmax; l++)
-            if (l < L) {
-              const double w = t[l] * inv;
-              v[l] += w;
-              wn = (l == nx) ? w : wn;
-            }
+      };
+      int bf = 0;
+      const bool dbl = a.nbuf == 2;
+      if (a.use_tma && dbl && warp == 0 && (long)blockIdx.x < ntiles) fetch(blockIdx.x, 0);
+      for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x, bf = dbl ? bf ^ 1 : 0) {
+        double *xs = tile + bf * tile_doubles, *Es = xs + d * kEmTS, *ws = Es + a.Lmax * kEmTS;
+        // -- per-sample phase: thread t owns sample tl*128 + t
+        const long i = tl * kEmThreads + t;
+        const bool valid = i < n;
+        if (a.use_tma) {
+          if (warp == 0) {
+            if (!dbl) fetch(tl, 0);
+            else if (tl + gridDim.x < ntiles) fetch(tl + gridDim.x, bf ^ 1);
+          }
+          mbar_wait(&s_bar[bf], tma_phase[bf]);
+          tma_phase[bf] ^= 1u;
         } else {
-          const double w = 1.0 / L;
-          v[kEmLmax + 1] += 1.0;
+          // coalesced loads: this thread's column of the tile, eight rows in flight at a time
 #pragma unroll
-          for (int l = 0; l < kEmLmax; l++)
-            if (l < L) v[l] += w;
-          wn = w;
+          for (int j = 0; j < DMAX; j++)
+            if (j < d) xs[j * kEmTS + t] = __ldcg(a.xT + (size_t)j * np + i);
+          for (int l0 = 0; l0 < L; l0 += 8) {
+            double e[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              e[k] = (l0 + k < L && !(dens && l0 + k == cc)) ? __ldcg(a.E + (size_t)s_slot[l0 + k] * np + i) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              if (l0 + k < L) Es[(l0 + k) * kEmTS + t] = e[k];
+          }
         }
-        __stcg(a.wnxt + i, wn);
+        if (dens) {
+          double xv[DMAX], r[DMAX];
 #pragma unroll
-        for (int j = 0; j < DMAX; j++) v[kEmLmax + 2 + j] = fma(wn, xv[j], v[kEmLmax + 2 + j]);
+          for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? xs[j * kEmTS + t] : 0.0;
+          const double enew = exp(fma(-0.5, solve_lower<DMAX, true>(s_rec, d, xv, r), s_rec[3]));
+          Es[cc * kEmTS + t] = enew;
+          if (valid) __stcg(a.E + (size_t)cslot * np + i, enew);
+        }
+        // sum_l lam_l E_il in component order (as the reference adds them); the loads of four
+        // components are in flight at a time, the additions stay sequential
+        double *__restrict__ Ecol = Es + t;
+        const double *__restrict__ lam = s_lam;
+        double sum = 0.0;
+        int l = 0;
+        for (; l + 4 <= L; l += 4) {
+          const double e0 = Ecol[(l + 0) * kEmTS], e1 = Ecol[(l + 1) * kEmTS], e2 = Ecol[(l + 2) * kEmTS],
+                       e3 = Ecol[(l + 3) * kEmTS];
+          const double a0 = lam[l], a1 = lam[l + 1], a2 = lam[l + 2], a3 = lam[l + 3];
+          sum = fma(a0, e0, sum);
+          sum = fma(a1, e1, sum);
+          sum = fma(a2, e2, sum);
+          sum = fma(a3, e3, sum);
+        }
+        for (; l < L; l++) sum = fma(lam[l], Ecol[l * kEmTS], sum);
+        if (valid) {
+          if (sum > 0) {  // the reference's guard (:855-866)
+            const double inv = 1.0 / sum;
+            ll += log(sum);
+            l = 0;
+            for (; l + 4 <= L; l += 4) {
+              const double e0 = Ecol[(l + 0) * kEmTS], e1 = Ecol[(l + 1) * kEmTS], e2 = Ecol[(l + 2) * kEmTS],
+                           e3 = Ecol[(l + 3) * kEmTS];
+              Ecol[(l + 0) * kEmTS] = (lam[l] * e0) * inv;
+              Ecol[(l + 1) * kEmTS] = (lam[l + 1] * e1) * inv;
+              Ecol[(l + 2) * kEmTS] = (lam[l + 2] * e2) * inv;
+              Ecol[(l + 3) * kEmTS] = (lam[l + 3] * e3) * inv;
+            }
+            for (; l < L; l++) Ecol[l * kEmTS] = (lam[l] * Ecol[l * kEmTS]) * inv;
+          } else {
+            nfb += 1.0;
+            const double w = 1.0 / L;
+            for (l = 0; l < L; l++) Ecol[l * kEmTS] = w;
+          }
+        } else {
+          for (l = 0; l < L; l++) Ecol[l * kEmTS] = 0.0;
+        }
+        const double wn = Es[nx * kEmTS + t];
+        ws[t] = wn;
+        if (valid) __stcg(a.wnxt + i, wn);
+        __syncthreads();
+        // -- reduction phase: thread (col, prt) sums every 4th sample of column col
+        if (col < L) {
+          double s4 = 0.0;
+#pragma unroll 8
+          for (int k = 0; k < kEmThreads / 4; k++) s4 += Es[col * kEmTS + prt + 4 * k];
+          acc_col += s4;
+        }
+        if (col < d) {
+          double s4 = 0.0;
+#pragma unroll 8
+          for (int k = 0; k < kEmThreads / 4; k++) s4 = fma(ws[prt + 4 * k], xs[col * kEmTS + prt + 4 * k], s4);
+          acc_s1 += s4;
+        }
+        __syncthreads();
+      }
+      // partial row: [colsum (Lmax) | loglik | fallbacks | S1 (d)]
+      acc_col += __shfl_xor_sync(0xffffffffu, acc_col, 1);
+      acc_col += __shfl_xor_sync(0xffffffffu, acc_col, 2);
+      acc_s1 += __shfl_xor_sync(0xffffffffu, acc_s1, 1);
+      acc_s1 += __shfl_xor_sync(0xffffffffu, acc_s1, 2);
+      if (prt == 0) {
+        part_col[(size_t)col * pstride] = (col < L) ? acc_col : 0.0;
+        if (col < d) part_col[(size_t)(kEmLmax + 2 + col) * pstride] = acc_s1;
+      }
+      ll = warp_sum(ll);
+      nfb = warp_sum(nfb);
+      if (lane == 0) {
+        s_red[warp * NRED + 0] = ll;
+        s_red[warp * NRED + 1] = nfb;
+      }
+      __syncthreads();
+      if (t < 2) {
+        double tot = 0.0;
+        for (int w = 0; w < kEmWarps; w++) tot += s_red[w * NRED + t];
+        part_col[(size_t)(kEmLmax + t) * pstride] = tot;
       }
       nv = kEmLmax + 2 + d;
-      block_reduce_store<NVC>(v, nv, s_red, part_row);
     }
 
     // ------------------------------------------------------------------ barrier + leader
+    const long long tk1 = clock64();
     if (barrier_arrive(ctrl, epoch)) {
-      if (nv > 0) leader_reduce(a.part, nv, s_tot);
-      if (threadIdx.x == 0) em_leader(ctrl, a, pass, s_tot);
-      barrier_release(ctrl, epoch);
+      const long long tl0 = clock64();
+      if (nv > 0) leader_reduce(a.part, nv, s_tot, s_chunk);
+      const long long tl1 = clock64();
+      em_leader_block<DMAX>(ctrl, a, pass, s_tot, s_lead);
+      const long long tl2 = clock64();
+      barrier_release(a.flags, epoch);
       __syncthreads();
+      if (threadIdx.x == 0) {
+        atomicAdd((unsigned long long *)&ctrl->dbg[2], (unsigned long long)(tl1 - tl0));
+        atomicAdd((unsigned long long *)&ctrl->dbg[3], (unsigned long long)(tl2 - tl1));
+        atomicAdd((unsigned long long *)&ctrl->dbg[1], (unsigned long long)(tl0 - tk1));
+      }
     } else {
-      barrier_wait(ctrl, epoch);
+      barrier_wait(a.flags, epoch);
+      if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&ctrl->dbg[4], (unsigned long long)(clock64() - tk1));
     }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+      atomicAdd((unsigned long long *)&ctrl->dbg[0], (unsigned long long)(tk1 - tk0));
+      if (pass == kPassScatter) atomicAdd((unsigned long long *)&ctrl->dbg[6], (unsigned long long)(tk1 - tk0));
+      if (pass == kPassDensRefresh || pass == kPassRefresh) atomicAdd((unsigned long long *)&ctrl->dbg[7], (unsigned long long)(tk1 - tk0));
+    }
+    const long long tk2 = clock64();
     // ------------------------------------------------------------------ reload the control state
     if (threadIdx.x == 0) {
       s_pass = ld_cg(&ctrl->pass);
@@ -528,6 +968,7 @@ __global__ void __launch_bounds__(kEmThreads) em_fit_kernel(EmArgs a) {
     for (int q = threadIdx.x; q < reclen; q += blockDim.x) s_rec[q] = ld_cg(&ctrl->rec[q]);
     __syncthreads();
     pass = s_pass;
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&ctrl->dbg[5], (unsigned long long)(clock64() - tk2));
     if (pass == kPassStop) break;
   }
 
@@ -535,11 +976,11 @@ __global__ void __launch_bounds__(kEmThreads) em_fit_kernel(EmArgs a) {
   if (a.w_out != nullptr) {
     const int L = s_L;
     for (long i = i0; i < n; i += stride) {
-      double s = 0.0;
-      for (int l = 0; l < L; l++) s += s_lam[l] * __ldcg(a.E + (size_t)s_slot[l] * np + i);
+      double sum = 0.0;
+      for (int l = 0; l < L; l++) sum += s_lam[l] * __ldcg(a.E + (size_t)s_slot[l] * np + i);
       for (int l = 0; l < L; l++) {
         const double e = __ldcg(a.E + (size_t)s_slot[l] * np + i);
-        a.w_out[(size_t)i * a.Lmax + l] = (s > 0) ? s_lam[l] * e / s : 1.0 / L;
+        a.w_out[(size_t)i * a.Lmax + l] = (sum > 0) ? s_lam[l] * e / sum : 1.0 / L;
       }
     }
   }
@@ -581,20 +1022,28 @@ using namespace amx;
 
 template <int DMAX>
 static int em_launch(EmArgs &a, int sms, float *ms) {
+  const char *nb = getenv("AMX_EM_NBUF"), *tm = getenv("AMX_EM_TMA");
+  a.nbuf = nb ? (atoi(nb) == 2 ? 2 : 1) : 1;
+  a.use_tma = tm ? (atoi(tm) != 0) : 1;  // measured on B200 (n=1e6, d=10, L=30): TMA 183 us/step, plain loads 244
+  if (!a.use_tma) a.nbuf = 1;
+  const size_t smem = a.nbuf * sizeof(double) * (size_t)(a.d + a.Lmax + 1) * kEmTS;
+  AMX_CUDA(cudaFuncSetAttribute(em_fit_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  AMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_fit_kernel<DMAX>, kEmThreads, 0));
-  if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM");
-  long want = (a.n + kEmThreads - 1) / kEmThreads;
+  AMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_fit_kernel<DMAX>, kEmThreads, smem));
+  if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM (%zu B of shared memory)", smem);
+  long want = a.npad / kEmThreads;  // tiles
   long cap = (long)sms * per_sm;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   if (grid < 1) grid = 1;
   AMX_CUDA(cudaMalloc(&a.part, sizeof(double) * (size_t)grid * kEmNV));
+  AMX_CUDA(cudaMalloc(&a.flags, sizeof(unsigned) * 8 * (size_t)grid));
+  AMX_CUDA(cudaMemsetAsync(a.flags, 0, sizeof(unsigned) * 8 * (size_t)grid, stream()));
   void *args[] = {&a};
   cudaEvent_t e0, e1;
   AMX_CUDA(cudaEventCreate(&e0));
   AMX_CUDA(cudaEventCreate(&e1));
   AMX_CUDA(cudaEventRecord(e0, stream()));
-  AMX_CUDA(cudaLaunchCooperativeKernel((void *)em_fit_kernel<DMAX>, dim3(grid), dim3(kEmThreads), args, 0, stream()));
+  AMX_CUDA(cudaLaunchCooperativeKernel((void *)em_fit_kernel<DMAX>, dim3(grid), dim3(kEmThreads), args, smem, stream()));
   count_launch();
   AMX_CUDA(cudaEventRecord(e1, stream()));
   AMX_CUDA(cudaEventSynchronize(e1));
@@ -629,12 +1078,15 @@ static int em_fit_impl(int d, long n, const double *x_dev, int Lmax, int maxit, 
   a.Lmax = Lmax;
   a.maxit = maxit;
   a.n = n;
-  a.npad = (n + 31) / 32 * 32;
+  a.npad = (n + kEmThreads - 1) / kEmThreads * kEmThreads;  // whole tiles; the padding is zero and carries no weight
   a.x = x_dev;
   int *idx_dev = nullptr;
   AMX_CUDA(cudaMalloc(&a.xT, sizeof(double) * (size_t)d * a.npad));
   AMX_CUDA(cudaMalloc(&a.E, sizeof(double) * (size_t)Lmax * a.npad));
   AMX_CUDA(cudaMalloc(&a.wnxt, sizeof(double) * (size_t)a.npad));
+  AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, stream()));
+  AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, stream()));
+  AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, stream()));
   AMX_CUDA(cudaMalloc(&a.ctrl, sizeof(EmCtrl)));
   AMX_CUDA(cudaMemsetAsync(a.ctrl, 0, sizeof(EmCtrl), stream()));
   AMX_CUDA(cudaMalloc(&idx_dev, sizeof(int) * Lmax));
@@ -683,8 +1135,11 @@ static int em_fit_impl(int d, long n, const double *x_dev, int Lmax, int maxit, 
     res->flops = c->flops;
     res->bytes = 8.0 * d * (double)n * (double)c->comp_steps;
   }
+  if (getenv("AMX_EM_DEBUG"))
+    fprintf(stderr, "[em dbg] cycles: block0 data pass %lld | leader: arrive-skew %lld reduce %lld logic %lld | block0 wait %lld reload %lld (phases ~%ld) | scatter passes %lld refresh passes %lld\n",
+            c->dbg[0], c->dbg[1], c->dbg[2], c->dbg[3], c->dbg[4], c->dbg[5], 2 * c->comp_steps, c->dbg[6], c->dbg[7]);
   const int status = c->status;
-  cudaFree(a.xT); cudaFree(a.E); cudaFree(a.wnxt); cudaFree(a.ctrl); cudaFree(idx_dev); cudaFree(a.part);
+  cudaFree(a.xT); cudaFree(a.E); cudaFree(a.wnxt); cudaFree(a.ctrl); cudaFree(idx_dev); cudaFree(a.part); cudaFree(a.flags);
   cudaFree(a.trace_L); cudaFree(a.trace_ann); cudaFree(a.trace_loglik); cudaFree(a.trace_cost); cudaFree(a.w_out);
   if (status) return fail(status, "EM fit: scatter matrix not positive definite");
   return AMX_OK;

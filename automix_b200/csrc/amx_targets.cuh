@@ -20,12 +20,12 @@ enum TargetKind { kTargetGaussMix = 1, kTargetQuad = 2, kTargetCoal = 3, kTarget
 // Solve T r = x - mu for the lower-triangular factor in a family record and return |r|^2.
 // (forward substitution of lnormprob, automix.c:1735-1747, with the diagonal divisions
 // replaced by multiplications with the precomputed reciprocals.)
-template <int DMAX>
+template <int DMAX, bool UNROLL = (DMAX <= kRegArrayMax)>
 __device__ __forceinline__ double solve_lower(const double *rec, int d, const double (&x)[DMAX],
                                               double (&r)[DMAX]) {
   const double *mu = rec + AMX_REC_HEAD, *rd = mu + d, *T = rd + d;
   double q = 0.0;
-  if constexpr (DMAX <= kRegArrayMax) {
+  if constexpr (UNROLL) {
 #pragma unroll
     for (int i = 0; i < DMAX; i++) {
       if (i < d) {
