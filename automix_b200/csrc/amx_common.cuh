@@ -40,6 +40,8 @@ __device__ __forceinline__ double max_m(double a, double b) { return a > b ? a :
 __device__ __forceinline__ double min_m(double a, double b) { return a < b ? a : b; }
 // Metropolis-Hastings acceptance probability exp(max(-30, min(0, dl))) (:612, :1063, :1247)
 __device__ __forceinline__ double mh_prob(double dl) { return exp(max_m(-30.0, min_m(0.0, dl))); }
+// u < mh_prob(dl), without the exponential when dl >= 0 (exp(0) = 1 > u for every u in [0,1)); NaN -> reject
+__device__ __forceinline__ bool mh_accept(double u, double dl) { return (dl >= 0.0) ? true : (u < exp(max_m(-30.0, dl))); }
 
 // Small arrays live in registers only if every index is a compile-time constant; these
 // accessors turn a run-time index into a select chain for small N and a plain (local

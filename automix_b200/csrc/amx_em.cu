@@ -669,14 +669,15 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         double xv[DMAX], r[DMAX];
 #pragma unroll
         for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? __ldcg(a.xT + (size_t)j * np + i) : 0.0;
-        const double lpd = fma(-0.5, solve_lower<DMAX, true>(s_rec, d, xv, r), s_rec[3]);
+        const double lpd = fma(-0.5, solve_lower<DMAX, (DMAX <= 12)>(s_rec, d, xv, r), s_rec[3]);
         __stcg(a.E + (size_t)slot * np + i, exp(lpd));
       }
       nv = 0;
     } else if (pass == kPassScatter) {
       // ---- S2 = sum_i wnxt_i (x_i - mu)(x_i - mu)^T, rows split over two thread groups when DMAX > 8
+      constexpr bool kBigD = DMAX > 12;  // entry-parallel scatter from the shared tile (below)
       constexpr int NLO = RSPLIT * (RSPLIT + 1) / 2, NHI = TRI - NLO;
-      constexpr int NACC = NLO > NHI ? NLO : NHI;
+      constexpr int NACC = kBigD ? (TRI + kEmThreads - 1) / kEmThreads : (NLO > NHI ? NLO : NHI);
       double acc[NACC];  // one row group per thread: [0,RSPLIT) for threads 0..63, [RSPLIT,DMAX) for 64..127
 #pragma unroll
       for (int q = 0; q < NACC; q++) acc[q] = 0.0;
@@ -695,7 +696,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
           tma_load_row(xs + j * kEmTS, (j < d ? a.xT + (size_t)j * np : a.wnxt) + tl * kEmThreads, kEmThreads * 8,
                        &s_bar[st]);
       };
-      if (!a.use_tma) {
+      if (!a.use_tma && !kBigD) {
         // coalesced loads: thread t reads sample tl*128+t of every row (one 1 KB request per warp-row);
         // with DMAX > 8 the two row groups each read samples tt and tt+64
         for (long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
@@ -741,17 +742,38 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
           }
         }
       }
-      if (a.use_tma && warp == 0)
+      const bool tma_sc = a.use_tma || kBigD;
+      if (tma_sc && warp == 0)
         for (int q = 0; q < NST - 1; q++)
           if ((long)blockIdx.x + (long)q * gridDim.x < ntiles) fetch(blockIdx.x + (long)q * gridDim.x, q);
       int st = 0;
-      for (long tl = blockIdx.x; a.use_tma && tl < ntiles; tl += gridDim.x) {
+      for (long tl = blockIdx.x; tma_sc && tl < ntiles; tl += gridDim.x) {
         const long ahead = tl + (long)(NST - 1) * gridDim.x;
         if (warp == 0 && ahead < ntiles) fetch(ahead, (st + NST - 1) % NST);  // that stage was drained last iteration
         mbar_wait(&s_bar[st], tma_phase[st]);
         tma_phase[st] ^= 1u;
         const double *xs = tile + st * stage_doubles, *ws = xs + d * kEmTS;
-        if constexpr (DMAX <= 8) {
+        if constexpr (kBigD) {
+          // d > 12: too many triangle entries for registers per sample.  Thread e owns entries e, e+128, ...
+          // of the packed triangle and walks the 128 samples of the tile in shared memory.
+          const int tri_d = d * (d + 1) / 2;
+#pragma unroll
+          for (int q = 0; q < NACC; q++) {
+            const int e = t + q * kEmThreads;
+            if (e < tri_d) {
+              int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+              while ((j + 1) * (j + 2) / 2 <= e) j++;
+              while (j * (j + 1) / 2 > e) j--;
+              const int k = e - j * (j + 1) / 2;
+              const double *xj = xs + j * kEmTS, *xk = xs + k * kEmTS;
+              const double mj = mu[j], mk = mu[k];
+              double sacc = 0.0;
+#pragma unroll 4
+              for (int i2 = 0; i2 < kEmThreads; i2++) sacc = fma(ws[i2] * (xj[i2] - mj), xk[i2] - mk, sacc);
+              acc[q] += sacc;
+            }
+          }
+        } else if constexpr (DMAX <= 8) {
           scatter_rows<DMAX, 0, DMAX>(acc, xs, mu, ws[t], t, d);  // padding samples carry w = 0
         } else {
           const int tt = t & 63;
@@ -766,6 +788,14 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         __syncthreads();  // everyone is done with this stage before it is refilled
         st = (st + 1 == NST) ? 0 : st + 1;
       }
+      nv = d * (d + 1) / 2;  // rows j<d of the packed triangle are its first tri(d) entries
+      if constexpr (kBigD) {
+#pragma unroll
+        for (int q = 0; q < NACC; q++) {
+          const int e = t + q * kEmThreads;
+          if (e < nv) part_col[(size_t)e * pstride] = acc[q];
+        }
+      } else {
       // warps 0,1 hold rows [0,RSPLIT) at s_red[..][q]; warps 2,3 hold the rest at s_red[..][NLO + q]
 #pragma unroll
       for (int q = 0; q < NACC; q++) {
@@ -774,7 +804,6 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         if (lane == 0 && dst < NRED) s_red[warp * NRED + dst] = r;
       }
       __syncthreads();
-      nv = d * (d + 1) / 2;  // rows j<d of the packed triangle are its first tri(d) entries
       for (int q = t; q < nv; q += blockDim.x) {
         double tot = 0.0;
         if (DMAX <= 8) {
@@ -785,6 +814,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
           tot = s_red[2 * NRED + q] + s_red[3 * NRED + q];
         }
         part_col[(size_t)q * pstride] = tot;
+      }
       }
     } else if (pass == kPassDensRefresh || pass == kPassRefresh) {
       // ---- (new density column,) responsibilities, column sums, log-likelihood, next first moment
@@ -843,7 +873,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
           double xv[DMAX], r[DMAX];
 #pragma unroll
           for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? xs[j * kEmTS + t] : 0.0;
-          const double enew = exp(fma(-0.5, solve_lower<DMAX, true>(s_rec, d, xv, r), s_rec[3]));
+          const double enew = exp(fma(-0.5, solve_lower<DMAX, (DMAX <= 12)>(s_rec, d, xv, r), s_rec[3]));
           Es[cc * kEmTS + t] = enew;
           if (valid) __stcg(a.E + (size_t)cslot * np + i, enew);
         }
@@ -1016,6 +1046,26 @@ __global__ void __launch_bounds__(kEmThreads) autorj_moment_kernel(int d, long n
   block_reduce_store<NVAL>(acc, nv, s_red, part + (size_t)blockIdx.x * kEmNV);
 }
 
+// d > 12: one thread per entry of the mean / packed triangle, samples in order (n = 1000 d in the product)
+__global__ void __launch_bounds__(256) autorj_generic_kernel(int d, long n, const double *x, const double *mu,
+                                                             double *out) {
+  const int nv = mu ? d * (d + 1) / 2 : d;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nv; e += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    if (mu == nullptr) {
+      for (long i = 0; i < n; i++) acc += x[i * d + e];
+    } else {
+      int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((j + 1) * (j + 2) / 2 <= e) j++;
+      while (j * (j + 1) / 2 > e) j--;
+      const int k = e - j * (j + 1) / 2;
+      const double mj = mu[j], mk = mu[k];
+      for (long i = 0; i < n; i++) acc = fma(x[i * d + j] - mj, x[i * d + k] - mk, acc);
+    }
+    out[e] = acc;
+  }
+}
+
 }  // namespace amx
 
 using namespace amx;
@@ -1102,7 +1152,8 @@ static int em_fit_impl(int d, long n, const double *x_dev, int Lmax, int maxit, 
   if (d <= 4) rc = em_launch<4>(a, sms, &ms);
   else if (d <= 8) rc = em_launch<8>(a, sms, &ms);
   else if (d <= 12) rc = em_launch<12>(a, sms, &ms);
-  else return fail(AMX_EINVAL, "amx_em_fit: d=%d > 12 is not built yet", d);
+  else if (d <= 20) rc = em_launch<20>(a, sms, &ms);
+  else rc = em_launch<32>(a, sms, &ms);
   if (rc) return rc;
   std::vector<char> hc(sizeof(EmCtrl));
   AMX_CUDA(cudaMemcpy(hc.data(), a.ctrl, sizeof(EmCtrl), cudaMemcpyDeviceToHost));
@@ -1185,7 +1236,7 @@ int amx_em_fit(int d, long n, const double *x, int Lmax, int maxit, const int *i
 
 int amx_autorj_fit(int d, long n, const double *x, double *wt, double *mean, double *tri) {
   if (int rc = require_device()) return rc;
-  if (d < 1 || d > 12 || n < 2 || !x) return fail(AMX_EINVAL, "amx_autorj_fit: need 1<=d<=12, n>=2");
+  if (d < 1 || d > kEmDmax || n < 2 || !x) return fail(AMX_EINVAL, "amx_autorj_fit: need 1<=d<=%d, n>=2", kEmDmax);
   double *x_dev = nullptr, *part = nullptr, *mu_dev = nullptr;
   const unsigned grid = (unsigned)((n + kEmThreads - 1) / kEmThreads < 592 ? (n + kEmThreads - 1) / kEmThreads : 592);
   AMX_CUDA(cudaMalloc(&x_dev, sizeof(double) * (size_t)n * d));
@@ -1196,18 +1247,30 @@ int amx_autorj_fit(int d, long n, const double *x, double *wt, double *mean, dou
   const int tlen = d * (d + 1) / 2;
   for (int phase = 0; phase < 2; phase++) {
     const double *mu_arg = phase ? mu_dev : nullptr;
-    if (d <= 4) autorj_moment_kernel<4><<<grid, kEmThreads, 0, stream()>>>(d, n, x_dev, mu_arg, part);
-    else autorj_moment_kernel<12><<<grid, kEmThreads, 0, stream()>>>(d, n, x_dev, mu_arg, part);
-    count_launch();
-    AMX_CUDA(cudaGetLastError());
-    AMX_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, stream()));
-    AMX_CUDA(cudaStreamSynchronize(stream()));
     const int nv = phase ? tlen : d;
-    for (int q = 0; q < nv; q++) {
-      double t = 0.0;
-      for (unsigned b = 0; b < grid; b++) t += hp[(size_t)b * kEmNV + q];
-      if (phase == 0) mean[q] = t / (double)n;
-      else tri[q] = t / (double)(n - 1);
+    if (d > 12) {  // entry-parallel, samples in order
+      autorj_generic_kernel<<<(nv + 255) / 256, 256, 0, stream()>>>(d, n, x_dev, mu_arg, part);
+      count_launch();
+      AMX_CUDA(cudaGetLastError());
+      AMX_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * nv, cudaMemcpyDeviceToHost, stream()));
+      AMX_CUDA(cudaStreamSynchronize(stream()));
+      for (int q = 0; q < nv; q++) {
+        if (phase == 0) mean[q] = hp[q] / (double)n;
+        else tri[q] = hp[q] / (double)(n - 1);
+      }
+    } else {
+      if (d <= 4) autorj_moment_kernel<4><<<grid, kEmThreads, 0, stream()>>>(d, n, x_dev, mu_arg, part);
+      else autorj_moment_kernel<12><<<grid, kEmThreads, 0, stream()>>>(d, n, x_dev, mu_arg, part);
+      count_launch();
+      AMX_CUDA(cudaGetLastError());
+      AMX_CUDA(cudaMemcpyAsync(hp.data(), part, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, stream()));
+      AMX_CUDA(cudaStreamSynchronize(stream()));
+      for (int q = 0; q < nv; q++) {
+        double t = 0.0;
+        for (unsigned b = 0; b < grid; b++) t += hp[(size_t)b * kEmNV + q];
+        if (phase == 0) mean[q] = t / (double)n;
+        else tri[q] = t / (double)(n - 1);
+      }
     }
     if (phase == 0) AMX_CUDA(cudaMemcpyAsync(mu_dev, mean, sizeof(double) * d, cudaMemcpyHostToDevice, stream()));
   }

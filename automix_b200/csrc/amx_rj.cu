@@ -89,9 +89,28 @@ __device__ __forceinline__ void open_stream<TapeStream>(TapeStream &u, const RjL
   u.open(a.tape, a.tape_stride, (unsigned long long)id, consumed);
 }
 
+// One out-of-line copy of the plug-in evaluation per kernel: the sweep calls it from three places, and
+// inlining all three made the kernel ~130 KB of SASS (instruction-fetch stalls were as frequent as issues).
+#ifndef AMX_RJ_EVAL_INLINE
+#define AMX_RJ_EVAL_INLINE 1  // measured on B200: out-of-line 3.9e9 chain-sweeps/s, inline 4.6e9 (toy1)
+#endif
+#ifndef AMX_RJ_MIN_BLOCKS
+#define AMX_RJ_MIN_BLOCKS 4
+#endif
+template <class CFG, class TGT>
+#if AMX_RJ_EVAL_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+    double
+    eval_target(const TGT &T, int k, const double (&x)[CFG::DMAX]) {
+  return T.template eval<CFG::DMAX>(k, x);
+}
+
 // ---- the fused sweep kernel ------------------------------------------------------------------
 template <class CFG, class TGT, class RNG>
-__global__ void __launch_bounds__(kRjThreads) rj_sweep_kernel(RjLaunch a, int staged) {
+__global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCKS : 1)) rj_sweep_kernel(RjLaunch a, int staged) {
   extern __shared__ double smem[];
   __shared__ unsigned s_hist[kRjWarps][CFG::NMAX];
   __shared__ int s_clp[AMX_MAX_MODELS];
@@ -130,20 +149,20 @@ __global__ void __launch_bounds__(kRjThreads) rj_sweep_kernel(RjLaunch a, int st
     const int d = P.h->dims[c.k];
     if (sweep_i % 10ull == 0ull) {  // block move every 10th sweep (:95, :148)
       rwm_block_propose(c, P, u);
-      const double lpn = T.template eval<CFG::DMAX>(c.k, c.thn);
+      const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
       rwm_block_finish(c, P, u, lpn);
       c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
     } else {
       sync_proposal(c, d);
       for (int j = 0; j < d; j++) {
         rwm_coord_propose(c, P, u, j);
-        const double lpn = T.template eval<CFG::DMAX>(c.k, c.thn);
+        const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
         rwm_coord_finish(c, u, j, lpn);
       }
       c.flops += (unsigned)(d * (s_clp[c.k] + 12));
     }
     rj_propose(c, P, u, a.gam[s], 0, s_clp);
-    const double lpn = T.template eval<CFG::DMAX>(c.kn, c.thn);
+    const double lpn = eval_target<CFG, TGT>(T, c.kn, c.thn);
     rj_finish(c, P, u, lpn, a.adapt != 0);
     if (c.lp != c.lp) status |= 2;
 

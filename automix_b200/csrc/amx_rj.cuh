@@ -69,7 +69,7 @@ __device__ __forceinline__ void rwm_block_propose(ChainRegs<CFG> &c, const Propo
 template <class CFG, class U>
 __device__ __forceinline__ void rwm_block_finish(ChainRegs<CFG> &c, const ProposalView &P, U &u, double lpn) {
   const int d = P.h->dims[c.k];
-  if (u.next() < mh_prob(lpn - c.lp)) {
+  if (mh_accept(u.next(), lpn - c.lp)) {
     c.acc_b++;
     if constexpr (CFG::DMAX <= kRegArrayMax) {
 #pragma unroll
@@ -88,7 +88,7 @@ __device__ __forceinline__ void rwm_coord_propose(ChainRegs<CFG> &c, const Propo
 }
 template <class CFG, class U>
 __device__ __forceinline__ void rwm_coord_finish(ChainRegs<CFG> &c, U &u, int j, double lpn) {
-  if (u.next() < mh_prob(lpn - c.lp)) {
+  if (mh_accept(u.next(), lpn - c.lp)) {
     c.acc_s++;
     aset(c.th, j, aget(c.thn, j));
     c.lp = lpn;
@@ -251,7 +251,7 @@ __device__ __forceinline__ void rj_finish(ChainRegs<CFG> &c, const ProposalView 
   lr += c.t_alloc;
   lr += c.t_wt;
   lr += c.t_det;
-  if (u.next() < mh_prob(lr)) {
+  if (mh_accept(u.next(), lr)) {
     const int dn = P.h->dims[c.kn];
     if constexpr (CFG::DMAX <= kRegArrayMax) {
 #pragma unroll

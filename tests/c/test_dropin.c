@@ -165,6 +165,46 @@ static void test_device_plugin(void) {
   amx_target_destroy(t);
 }
 
+/* BASELINE config 3: coal-mining change points (usercpt.c), models with 1..6 change points.
+ * Published posterior model probabilities: 0.058 0.250 0.296 0.234 0.118 0.044 (thesis p.177);
+ * the reference run of SURVEY.md 6.2 gave 0.0589 0.2581 0.3006 0.2244 0.1181 0.0400. */
+static void test_coalmine(void) {
+  printf("coal-mining change points with the __device__ plug-in ...\n");
+  const double want[6] = {0.058, 0.250, 0.296, 0.234, 0.118, 0.044};
+  int dims[6];
+  double init[48];
+  int pos = 0;
+  for (int k = 0; k < 6; k++) {
+    dims[k] = 2 * k + 3;
+    for (int j = 0; j < k + 2; j++) init[pos + j] = 1.0 / 200.0;                      /* usercpt.c:35-37 */
+    for (int j = 1; j < k + 2; j++) init[pos + k + 1 + j] = (40907.0 * j) / (k + 2);  /* usercpt.c:38-40 */
+    pos += dims[k];
+  }
+  amx_target *t = amx_target_coalmine();
+  CHECK(t != NULL, "amx_target_coalmine: %s", amx_last_error());
+  amSampler am;
+  initAMSampler(&am, 6, dims, NULL, init);
+  amx_sampler_set_target(&am, t);
+  amx_sampler_set_seed(&am, 1851);
+  amx_sampler_set_chains(&am, 16384, 1);
+  estimate_conditional_probs(&am, 100000);
+  burn_samples(&am, 2000);
+  rjmcmc_samples(&am, 2000);
+  const amx_sampler_stats *s = amx_sampler_stats_get(&am);
+  CHECK(s->last_error == 0, "GPU stage failed: %s", amx_last_error());
+  double tot = 0;
+  for (int k = 0; k < 6; k++) tot += (double)s->visits[k];
+  printf("  fitted L = (%d %d %d %d %d %d); P(k) =", am.jd.nMixComps[0], am.jd.nMixComps[1], am.jd.nMixComps[2],
+         am.jd.nMixComps[3], am.jd.nMixComps[4], am.jd.nMixComps[5]);
+  for (int k = 0; k < 6; k++) printf(" %.4f", s->visits[k] / tot);
+  printf("\n  stage times: RWM %.0f ms, EM %.0f ms, RJ %.0f ms (kernels)\n", s->kernel_ms_rwm, s->kernel_ms_em,
+         s->kernel_ms_rj);
+  for (int k = 0; k < 6; k++) CHECK(fabs(s->visits[k] / tot - want[k]) < 0.03, "P(model %d) = %.4f, published %.3f", k, s->visits[k] / tot, want[k]);
+  CHECK(tot == 16384.0 * 2000.0, "visits add up");
+  freeAMSampler(&am);
+  amx_target_destroy(t);
+}
+
 int main(void) {
   amSampler bad;
   int d1 = 1;
@@ -181,6 +221,7 @@ int main(void) {
   test_sampler("Beta(2,2) sampler", lp_beta22, 0.5, 0.5, 0.2236, 0.0, 1.0);
   test_two_models();
   test_device_plugin();
+  test_coalmine();
   printf(failures ? "FAILED (%d)\n" : "OK\n", failures);
   return failures ? 1 : 0;
 }

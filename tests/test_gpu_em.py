@@ -83,7 +83,8 @@ def test_product_sized_fit_against_reference_golden(amx, name, k):
     assert r["L"] == int(g["mix_ncomp"][k])
 
 
-@pytest.mark.parametrize("d,n,L", [(1, 3000, 8), (4, 5000, 10), (7, 6000, 12), (10, 20000, 30), (12, 9000, 16)])
+@pytest.mark.parametrize("d,n,L", [(1, 3000, 8), (4, 5000, 10), (7, 6000, 12), (10, 20000, 30), (12, 9000, 16),
+                                   (13, 6000, 10), (20, 8000, 12), (32, 4000, 6)])
 def test_shapes_against_oracle(amx, orc, d, n, L):
     rng = np.random.default_rng(d)
     cents = rng.normal(size=(3, d)) * 4
@@ -121,6 +122,15 @@ def test_autorj_against_reference_golden(amx):
     g = cases.load_golden("em3d")
     r = amx.autorj_fit(g["x"])
     assert _rel(r["mu"], g["autorj_mu"]) < STEP_RTOL and _rel(r["B"], g["autorj_B"]) < STEP_RTOL
+
+
+@pytest.mark.parametrize("d", [3, 13, 24])
+def test_autorj_against_oracle(amx, orc, d):
+    rng = np.random.default_rng(d)
+    A = rng.normal(size=(d, d))
+    x = rng.normal(size=(1000 * d // 4, d)) @ A.T + rng.normal(size=d) * 5
+    r, o = amx.autorj_fit(x), orc.fit_autorj(x)
+    assert _rel(r["mu"], o["mu"]) < 1e-12 and _rel(r["B"], o["B"]) < 1e-11
 
 
 def test_rejects_bad_arguments(amx):
