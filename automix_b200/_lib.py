@@ -46,7 +46,7 @@ EXPORTS = [
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
     "amx_rj_set_tape", "amx_rj_set_chain_base", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
     "amx_rj_collect", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_em_fit", "amx_em_fit_dev",
-    "amx_em_draw_init", "amx_autorj_fit", "amx_rwm_adapt", "amx_fam_plan", "amx_fam_pack",
+    "amx_em_draw_init", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
 ]
 
 

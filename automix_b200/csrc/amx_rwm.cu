@@ -375,15 +375,23 @@ static int rwm_host_run(const amx_target *t, RwmArgs &a) {
 
 using namespace amx;
 
-extern "C" int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long nchains, const double *init,
-                             uint64_t seed, const double *tape, long tape_stride, double *sig_out,
-                             double *samples_out, double *sig_trace0, double *acc_trace0, double *kernel_ms) {
-  if (int rc = require_device()) return rc;
-  if (!t || model_k < 0 || model_k >= t->d.nmodels || nchains < 1 || nsweep2 < 1 || !init || !sig_out || !samples_out)
-    return fail(AMX_EINVAL, "amx_rwm_adapt: bad arguments");
-  const int d = t->d.dims[model_k];
+// One stage-1 run = allocate + enqueue (start) and wait + read back (finish); splitting the two lets
+// the runs of all models be in flight at once on separate streams (amx_rwm_adapt_all).
+struct RwmJob {
   RwmArgs a;
-  memset(&a, 0, sizeof(a));
+  double *init_dev, *gtab, *tape_dev, *sig_dev, *samp_dev, *tr_dev;
+  int *status_dev;
+  cudaEvent_t e0, e1;
+  long nstore;
+  int ntr;
+  bool host_target;
+};
+
+static int rwm_job_start(const amx_target *t, int model_k, int nsweep2, long nchains, const double *init,
+                         uint64_t seed, const double *tape, long tape_stride, RwmJob &J) {
+  memset(&J, 0, sizeof(J));
+  const int d = t->d.dims[model_k];
+  RwmArgs &a = J.a;
   int nsw = nsweep2 > 10000 * d ? nsweep2 : 10000 * d;  // :579-582
   a.nburn = nsw / 10;
   a.nsweepr = nsw + a.nburn;
@@ -393,58 +401,144 @@ extern "C" int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long
   a.d = d;
   a.nchains = nchains;
   a.seed = seed;
-  const long nstore = 1000L * d;
-  const int ntr = a.nsweepr / 100;
-  double *init_dev = nullptr, *gtab = nullptr, *tape_dev = nullptr, *sig_dev = nullptr, *samp_dev = nullptr,
-         *tr_dev = nullptr;
-  int *status_dev = nullptr;
-  AMX_CUDA(cudaMalloc(&init_dev, sizeof(double) * d));
-  AMX_CUDA(cudaMemcpyAsync(init_dev, init, sizeof(double) * d, cudaMemcpyHostToDevice, stream()));
-  AMX_CUDA(cudaMalloc(&gtab, sizeof(double) * a.nsweepr));
-  AMX_CUDA(cudaMalloc(&sig_dev, sizeof(double) * (size_t)nchains * d));
-  AMX_CUDA(cudaMalloc(&samp_dev, sizeof(double) * (size_t)nchains * nstore * d));
-  AMX_CUDA(cudaMalloc(&tr_dev, sizeof(double) * (size_t)2 * (ntr + 1) * d));
-  AMX_CUDA(cudaMalloc(&status_dev, sizeof(int)));
-  AMX_CUDA(cudaMemsetAsync(status_dev, 0, sizeof(int), stream()));
+  J.nstore = 1000L * d;
+  J.ntr = a.nsweepr / 100;
+  J.host_target = (t->d.kind == kTargetHostScalar || t->d.kind == kTargetHostBatched);
+  AMX_CUDA(cudaMalloc(&J.init_dev, sizeof(double) * d));
+  AMX_CUDA(cudaMemcpyAsync(J.init_dev, init, sizeof(double) * d, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMalloc(&J.gtab, sizeof(double) * a.nsweepr));
+  AMX_CUDA(cudaMalloc(&J.sig_dev, sizeof(double) * (size_t)nchains * d));
+  AMX_CUDA(cudaMalloc(&J.samp_dev, sizeof(double) * (size_t)nchains * J.nstore * d));
+  AMX_CUDA(cudaMalloc(&J.tr_dev, sizeof(double) * (size_t)2 * (J.ntr + 1) * d));
+  AMX_CUDA(cudaMalloc(&J.status_dev, sizeof(int)));
+  AMX_CUDA(cudaMemsetAsync(J.status_dev, 0, sizeof(int), stream()));
   if (tape) {
-    AMX_CUDA(cudaMalloc(&tape_dev, sizeof(double) * (size_t)tape_stride * nchains));
-    AMX_CUDA(cudaMemcpyAsync(tape_dev, tape, sizeof(double) * (size_t)tape_stride * nchains, cudaMemcpyHostToDevice, stream()));
+    AMX_CUDA(cudaMalloc(&J.tape_dev, sizeof(double) * (size_t)tape_stride * nchains));
+    AMX_CUDA(cudaMemcpyAsync(J.tape_dev, tape, sizeof(double) * (size_t)tape_stride * nchains, cudaMemcpyHostToDevice, stream()));
   }
-  a.init = init_dev;
-  a.gtab = gtab;
-  a.tape = tape_dev;
+  a.init = J.init_dev;
+  a.gtab = J.gtab;
+  a.tape = J.tape_dev;
   a.tape_stride = (unsigned long long)tape_stride;
-  a.sig_out = sig_dev;
-  a.samples_out = samp_dev;
-  a.sig_trace0 = tr_dev;
-  a.acc_trace0 = tr_dev + (size_t)(ntr + 1) * d;
-  a.status = status_dev;
-  rwm_gamma_kernel<<<(a.nsweepr + 255) / 256, 256, 0, stream()>>>(gtab, a.nsweepr);
+  a.sig_out = J.sig_dev;
+  a.samples_out = J.samp_dev;
+  a.sig_trace0 = J.tr_dev;
+  a.acc_trace0 = J.tr_dev + (size_t)(J.ntr + 1) * d;
+  a.status = J.status_dev;
+  rwm_gamma_kernel<<<(a.nsweepr + 255) / 256, 256, 0, stream()>>>(J.gtab, a.nsweepr);
   count_launch();
-  cudaEvent_t e0, e1;
-  AMX_CUDA(cudaEventCreate(&e0));
-  AMX_CUDA(cudaEventCreate(&e1));
-  AMX_CUDA(cudaEventRecord(e0, stream()));
+  AMX_CUDA(cudaEventCreate(&J.e0));
+  AMX_CUDA(cudaEventCreate(&J.e1));
+  AMX_CUDA(cudaEventRecord(J.e0, stream()));
   int rc;
-  if (t->d.kind == kTargetHostScalar || t->d.kind == kTargetHostBatched) rc = rwm_host_run(t, a);
+  if (J.host_target) rc = rwm_host_run(t, a);
   else rc = tape ? rwm_launch<TapeStream>(t, a) : rwm_launch<PhiloxStream>(t, a);
   if (rc) return rc;
-  AMX_CUDA(cudaEventRecord(e1, stream()));
-  AMX_CUDA(cudaEventSynchronize(e1));
+  AMX_CUDA(cudaEventRecord(J.e1, stream()));
+  return AMX_OK;
+}
+
+static int rwm_job_finish(RwmJob &J, double *sig_out, double *samples_out, double *sig_trace0, double *acc_trace0,
+                          double *kernel_ms) {
+  const int d = J.a.d;
+  const long nchains = J.a.nchains;
+  AMX_CUDA(cudaEventSynchronize(J.e1));
   float ms = 0;
-  AMX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  AMX_CUDA(cudaEventElapsedTime(&ms, J.e0, J.e1));
   if (kernel_ms) *kernel_ms = ms;
   int status = 0;
-  AMX_CUDA(cudaMemcpy(&status, status_dev, sizeof(int), cudaMemcpyDeviceToHost));
-  AMX_CUDA(cudaMemcpy(sig_out, sig_dev, sizeof(double) * (size_t)nchains * d, cudaMemcpyDeviceToHost));
-  AMX_CUDA(cudaMemcpy(samples_out, samp_dev, sizeof(double) * (size_t)nchains * nstore * d, cudaMemcpyDeviceToHost));
-  if (sig_trace0) AMX_CUDA(cudaMemcpy(sig_trace0, a.sig_trace0, sizeof(double) * (size_t)ntr * d, cudaMemcpyDeviceToHost));
-  if (acc_trace0) AMX_CUDA(cudaMemcpy(acc_trace0, a.acc_trace0, sizeof(double) * (size_t)ntr * d, cudaMemcpyDeviceToHost));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(init_dev); cudaFree(gtab); cudaFree(tape_dev); cudaFree(sig_dev); cudaFree(samp_dev); cudaFree(tr_dev);
-  cudaFree(status_dev);
+  AMX_CUDA(cudaMemcpy(&status, J.status_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  AMX_CUDA(cudaMemcpy(sig_out, J.sig_dev, sizeof(double) * (size_t)nchains * d, cudaMemcpyDeviceToHost));
+  AMX_CUDA(cudaMemcpy(samples_out, J.samp_dev, sizeof(double) * (size_t)nchains * J.nstore * d, cudaMemcpyDeviceToHost));
+  if (sig_trace0) AMX_CUDA(cudaMemcpy(sig_trace0, J.a.sig_trace0, sizeof(double) * (size_t)J.ntr * d, cudaMemcpyDeviceToHost));
+  if (acc_trace0) AMX_CUDA(cudaMemcpy(acc_trace0, J.a.acc_trace0, sizeof(double) * (size_t)J.ntr * d, cudaMemcpyDeviceToHost));
+  cudaEventDestroy(J.e0);
+  cudaEventDestroy(J.e1);
+  cudaFree(J.init_dev); cudaFree(J.gtab); cudaFree(J.tape_dev); cudaFree(J.sig_dev); cudaFree(J.samp_dev);
+  cudaFree(J.tr_dev); cudaFree(J.status_dev);
   if (status & 1) return fail(AMX_ETAPE, "injected uniform tape exhausted");
   if (status & 2) return fail(AMX_ENUMERIC, "a chain reached a NaN log-posterior");
   return AMX_OK;
+}
+
+extern "C" int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long nchains, const double *init,
+                             uint64_t seed, const double *tape, long tape_stride, double *sig_out,
+                             double *samples_out, double *sig_trace0, double *acc_trace0, double *kernel_ms) {
+  if (int rc = require_device()) return rc;
+  if (!t || model_k < 0 || model_k >= t->d.nmodels || nchains < 1 || nsweep2 < 1 || !init || !sig_out || !samples_out)
+    return fail(AMX_EINVAL, "amx_rwm_adapt: bad arguments");
+  RwmJob J;
+  if (int rc = rwm_job_start(t, model_k, nsweep2, nchains, init, seed, tape, tape_stride, J)) return rc;
+  return rwm_job_finish(J, sig_out, samples_out, sig_trace0, acc_trace0, kernel_ms);
+}
+
+// Stage 1 for every model at once: the models' chains are independent (the reference runs them one after
+// another, automix.c:163-176), so their kernels are enqueued on separate streams and overlap on the GPU.
+// init_flat / sig_out / samples_out are the per-model arrays concatenated in model order; sig_trace0 and
+// acc_trace0 are arrays of nmodels pointers (entries may be NULL).  kernel_ms: wall time of the whole stage.
+extern "C" int amx_rwm_adapt_all(const amx_target *t, int nsweep2, long nchains, const double *init_flat,
+                                 uint64_t seed, double *sig_out, double *samples_out, double **sig_trace0,
+                                 double **acc_trace0, double *kernel_ms) {
+  if (int rc = require_device()) return rc;
+  if (!t || nchains < 1 || nsweep2 < 1 || !init_flat || !sig_out || !samples_out)
+    return fail(AMX_EINVAL, "amx_rwm_adapt_all: bad arguments");
+  const int nm = t->d.nmodels;
+  const bool host = (t->d.kind == kTargetHostScalar || t->d.kind == kTargetHostBatched);
+  std::vector<RwmJob> jobs(nm);
+  std::vector<cudaStream_t> streams(nm, nullptr);
+  cudaStream_t saved = stream();
+  cudaEvent_t w0, w1;
+  AMX_CUDA(cudaEventCreate(&w0));
+  AMX_CUDA(cudaEventCreate(&w1));
+  AMX_CUDA(cudaEventRecord(w0, saved));
+  int rc = AMX_OK;
+  size_t off_i = 0, off_s = 0, off_x = 0;
+  std::vector<size_t> oi(nm), os(nm), ox(nm);
+  for (int k = 0; k < nm; k++) {
+    const int d = t->d.dims[k];
+    oi[k] = off_i; os[k] = off_s; ox[k] = off_x;
+    off_i += d;
+    off_s += (size_t)nchains * d;
+    off_x += (size_t)nchains * 1000 * d * d;
+  }
+  if (host) {  // callbacks run on the calling thread: one model after another
+    double tot = 0.0;
+    for (int k = 0; k < nm && rc == AMX_OK; k++) {
+      double ms = 0.0;
+      rc = amx_rwm_adapt(t, k, nsweep2, nchains, init_flat + oi[k], seed + 7919u * (uint64_t)k, nullptr, 0, sig_out + os[k],
+                         samples_out + ox[k], sig_trace0 ? sig_trace0[k] : nullptr, acc_trace0 ? acc_trace0[k] : nullptr, &ms);
+      tot += ms;
+    }
+    if (kernel_ms) *kernel_ms = tot;
+    cudaEventDestroy(w0);
+    cudaEventDestroy(w1);
+    return rc;
+  }
+  int started = 0;
+  for (int k = 0; k < nm && rc == AMX_OK; k++) {
+    if (cudaStreamCreateWithFlags(&streams[k], cudaStreamNonBlocking) != cudaSuccess) {
+      rc = fail(AMX_ECUDA, "stream creation failed");
+      break;
+    }
+    cudaStreamWaitEvent(streams[k], w0, 0);
+    amx_set_stream(streams[k]);
+    rc = rwm_job_start(t, k, nsweep2, nchains, init_flat + oi[k], seed + 7919u * (uint64_t)k, nullptr, 0, jobs[k]);
+    if (rc == AMX_OK) started++;
+  }
+  amx_set_stream(saved);
+  for (int k = 0; k < started; k++) {
+    int r2 = rwm_job_finish(jobs[k], sig_out + os[k], samples_out + ox[k], sig_trace0 ? sig_trace0[k] : nullptr,
+                            acc_trace0 ? acc_trace0[k] : nullptr, nullptr);
+    if (rc == AMX_OK) rc = r2;
+  }
+  for (int k = 0; k < nm; k++)
+    if (streams[k]) cudaStreamDestroy(streams[k]);
+  AMX_CUDA(cudaEventRecord(w1, saved));
+  AMX_CUDA(cudaEventSynchronize(w1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, w0, w1);
+  if (kernel_ms) *kernel_ms = ms;
+  cudaEventDestroy(w0);
+  cudaEventDestroy(w1);
+  return rc;
 }

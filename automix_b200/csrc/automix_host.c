@@ -337,25 +337,48 @@ void estimate_conditional_probs(amSampler *am, int nsweep2) {
   }
   const long P = e->rwm_chains > 0 ? e->rwm_chains : env_long("AMX_RWM_CHAINS", 1);
   const uint64_t seed = e->seed_set ? e->seed : (uint64_t)am->seed;
+  /* stage 1 for all models at once (reference :176, one model after another there): the models'
+   * chains are independent, their kernels overlap on the GPU */
+  size_t tot_s = 0, tot_x = 0, tot_i = 0;
+  size_t off_s[AMX_MAX_MODELS], off_x[AMX_MAX_MODELS];
+  for (int k = 0; k < nm; k++) {
+    const int d = jd->model_dims[k];
+    off_s[k] = tot_s;
+    off_x[k] = tot_x;
+    tot_s += (size_t)P * d;
+    tot_x += (size_t)P * 1000 * d * d;
+    tot_i += d;
+  }
+  double *sig_all = (double *)malloc(sizeof(double) * tot_s);
+  double *samples_all = (double *)malloc(sizeof(double) * tot_x);
+  double *init_all = (double *)malloc(sizeof(double) * tot_i);
+  double *tr_sig[AMX_MAX_MODELS], *tr_acc[AMX_MAX_MODELS];
+  {
+    size_t q = 0;
+    for (int k = 0; k < nm; k++) {
+      for (int i = 0; i < jd->model_dims[k]; i++) init_all[q++] = am->initRWM[k][i];
+      tr_sig[k] = cp->sig_k_rwm_summary[k][0];
+      tr_acc[k] = cp->nacc_ntry_rwm[k][0];
+    }
+  }
+  {
+    double ms = 0.0;
+    int rc = amx_rwm_adapt_all(tgt, nsweep2, P, init_all, seed, sig_all, samples_all, tr_sig, tr_acc, &ms);
+    e->stats.kernel_ms_rwm += ms;
+    free(init_all);
+    if (report(e, "amx_rwm_adapt_all", rc)) {
+      free(sig_all);
+      free(samples_all);
+      return;
+    }
+  }
   for (int k = 0; k < nm; k++) {
     const int d = jd->model_dims[k];
     const int tri = d * (d + 1) / 2;
     const long ns = 1000L * d;
-    const int nsw = nsweep2 > 10000 * d ? nsweep2 : 10000 * d;
-    const int rows = (nsw + nsw / 10) / 100;
-    double *sig = (double *)malloc(sizeof(double) * P * d);
-    double *samples = (double *)malloc(sizeof(double) * (size_t)P * ns * d);
-    double ms = 0.0;
-    /* stage 1: adaptive RWM (reference :176) */
-    int rc = amx_rwm_adapt(tgt, k, nsweep2, P, am->initRWM[k], seed + 7919u * (uint64_t)k, NULL, 0, sig, samples,
-                           cp->sig_k_rwm_summary[k][0], cp->nacc_ntry_rwm[k][0], &ms);
-    (void)rows;
-    e->stats.kernel_ms_rwm += ms;
-    if (report(e, "amx_rwm_adapt", rc)) {
-      free(sig);
-      free(samples);
-      return;
-    }
+    double *sig = sig_all + off_s[k];
+    double *samples = samples_all + off_x[k];
+    int rc = AMX_OK;
     double *fit = samples; /* chain 0 = the reference's single chain */
     if (P > 1) {           /* pool the tails of all chains into one n x d sample set */
       fit = (double *)malloc(sizeof(double) * (size_t)ns * d);
@@ -407,13 +430,17 @@ void estimate_conditional_probs(amSampler *am, int nsweep2) {
       }
     }
     if (fit != samples) free(fit);
-    free(sig);
-    free(samples);
     free(wt);
     free(mean);
     free(tr);
-    if (rc != AMX_OK) return;
+    if (rc != AMX_OK) {
+      free(sig_all);
+      free(samples_all);
+      return;
+    }
   }
+  free(sig_all);
+  free(samples_all);
   /* a new proposal invalidates a population built on the old one */
   if (e->rj) {
     amx_rj_destroy(e->rj);

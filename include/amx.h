@@ -222,6 +222,13 @@ int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long nchains,
                   long tape_stride, double *sig_out, double *samples_out,
                   double *sig_trace0, double *acc_trace0, double *kernel_ms);
 
+/* Stage 1 for every model at once, the models' kernels overlapping on separate streams.  init_flat,
+ * sig_out (nchains x d_k) and samples_out (nchains x 1000 d_k x d_k) are concatenated in model order;
+ * sig_trace0 / acc_trace0 are arrays of nmodels pointers (or NULL).  kernel_ms: device time of the stage. */
+int amx_rwm_adapt_all(const amx_target *t, int nsweep2, long nchains, const double *init_flat, uint64_t seed,
+                      double *sig_out, double *samples_out, double **sig_trace0, double **acc_trace0,
+                      double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif
