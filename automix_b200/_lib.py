@@ -275,14 +275,23 @@ class RjPopulation:
             lp[i], k[i], nre[i], lim[i] = s["lp"], s["k"], s["nreinit"], s["pkllim"]
         check(lib().amx_rj_set_state(self.h, first, n, _d(theta), _d(pk), _d(lp), _i(k), _i(nre), _d(lim), sweep_i))
 
-    def get_state(self, first=0, count=None):
+    def set_state_arrays(self, st, sweep_i, first=0):
+        """Upload chain states from chain-major host arrays (a dict as returned by get_state)."""
+        n = len(st["lp"])
+        check(lib().amx_rj_set_state(self.h, first, n, _d(st["theta"]), _d(st["pk"]), _d(st["lp"]), _i(st["k"]),
+                                     _i(st["nreinit"]), _d(st["pkllim"]), sweep_i))
+
+    def get_state(self, first=0, count=None, out=None):
         n = self.C - first if count is None else count
-        theta = np.zeros((n, self.dmax))
-        pk = np.zeros((n, self.nm))
-        lp = np.zeros(n)
-        k = np.zeros(n, np.int32)
-        nre = np.zeros(n, np.int32)
-        lim = np.zeros(n)
+        if out is not None:
+            theta, pk, lp, k, nre, lim = (out[q] for q in ("theta", "pk", "lp", "k", "nreinit", "pkllim"))
+        else:
+            theta = np.zeros((n, self.dmax))
+            pk = np.zeros((n, self.nm))
+            lp = np.zeros(n)
+            k = np.zeros(n, np.int32)
+            nre = np.zeros(n, np.int32)
+            lim = np.zeros(n)
         sw = C.c_ulonglong(0)
         check(lib().amx_rj_get_state(self.h, first, n, _d(theta), _d(pk), _d(lp), _i(k), _i(nre), _d(lim), C.byref(sw)))
         return dict(theta=theta, pk=pk, lp=lp, k=k, nreinit=nre, pkllim=lim, sweep_i=int(sw.value))

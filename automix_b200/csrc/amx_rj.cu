@@ -390,6 +390,22 @@ __global__ void __launch_bounds__(kRjThreads) rj_init_kernel(RjLaunch a, const d
   if (u.overrun()) atomicOr(a.status, 1);
 }
 
+// ---- chain-major (host API) <-> coordinate-major (device) state transposition ----------------------------
+__global__ void rj_state_scatter_kernel(RjState st, long first, long count, const double *theta_cm, const double *pk_cm) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= count) return;
+  for (int i = 0; i < st.dmax; i++) st.theta[(long)i * st.C + first + c] = theta_cm[c * st.dmax + i];
+  for (int j = 0; j < st.nmodels; j++) st.pk[(long)j * st.C + first + c] = pk_cm[c * st.nmodels + j];
+}
+__global__ void rj_state_gather_kernel(RjState st, long first, long count, double *theta_cm, double *pk_cm) {
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= count) return;
+  if (theta_cm)
+    for (int i = 0; i < st.dmax; i++) theta_cm[c * st.dmax + i] = st.theta[(long)i * st.C + first + c];
+  if (pk_cm)
+    for (int j = 0; j < st.nmodels; j++) pk_cm[c * st.nmodels + j] = st.pk[(long)j * st.C + first + c];
+}
+
 // ---- batched evaluation of a plug-in (amx_target_eval; also the target parity tests) --------------
 template <class TGT>
 __global__ void __launch_bounds__(kRjThreads) target_eval_kernel(const void *blob, int flags, long n,
@@ -429,6 +445,8 @@ struct amx_rj {
   cudaEvent_t e0, e1;
   double kernel_ms;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *pending;
+  double *stage_dev;  // chain-major staging for set/get_state
+  long stage_cap;
   // host-callback mode
   RjSplit sp;
   double *h_thn, *h_lpn;  // pinned mirrors
@@ -651,6 +669,7 @@ void amx_rj_destroy(amx_rj *rj) {
     cudaEventDestroy(pr.second);
   }
   delete rj->pending;
+  cudaFree(rj->stage_dev);
   cudaFree(rj->sp.thn); cudaFree(rj->sp.keval); cudaFree(rj->sp.lpn); cudaFree(rj->sp.kn); cudaFree(rj->sp.carry);
   if (rj->h_thn) cudaFreeHost(rj->h_thn);
   if (rj->h_lpn) cudaFreeHost(rj->h_lpn);
@@ -727,21 +746,26 @@ int amx_rj_set_state(amx_rj *rj, long first, long count, const double *theta, co
                      unsigned long long sweep_i) {
   if (!rj || first < 0 || count < 1 || first + count > rj->C) return fail(AMX_EINVAL, "amx_rj_set_state: range");
   RjState &s = rj->st;
-  // host arrays are chain-major; the device layout is coordinate-major
-  for (int i = 0; i < rj->dmax; i++) {
-    std::vector<double> col(count);
-    for (long c = 0; c < count; c++) col[c] = theta[c * rj->dmax + i];
-    AMX_CUDA(cudaMemcpy(s.theta + (size_t)i * rj->C + first, col.data(), sizeof(double) * count, cudaMemcpyHostToDevice));
+  // host arrays are chain-major; the device layout is coordinate-major: one contiguous copy, then a
+  // transposing kernel
+  const long need = count * (rj->dmax + rj->nm);
+  if (need > rj->stage_cap) {
+    cudaFree(rj->stage_dev);
+    rj->stage_dev = nullptr;
+    AMX_CUDA(cudaMalloc(&rj->stage_dev, sizeof(double) * need));
+    rj->stage_cap = need;
   }
-  for (int j = 0; j < rj->nm; j++) {
-    std::vector<double> col(count);
-    for (long c = 0; c < count; c++) col[c] = pk[c * rj->nm + j];
-    AMX_CUDA(cudaMemcpy(s.pk + (size_t)j * rj->C + first, col.data(), sizeof(double) * count, cudaMemcpyHostToDevice));
-  }
-  AMX_CUDA(cudaMemcpy(s.lp + first, lp, sizeof(double) * count, cudaMemcpyHostToDevice));
-  AMX_CUDA(cudaMemcpy(s.k + first, k, sizeof(int) * count, cudaMemcpyHostToDevice));
-  AMX_CUDA(cudaMemcpy(s.nreinit + first, nreinit, sizeof(int) * count, cudaMemcpyHostToDevice));
-  AMX_CUDA(cudaMemcpy(s.pkllim + first, pkllim, sizeof(double) * count, cudaMemcpyHostToDevice));
+  double *th_cm = rj->stage_dev, *pk_cm = rj->stage_dev + count * rj->dmax;
+  AMX_CUDA(cudaMemcpyAsync(th_cm, theta, sizeof(double) * count * rj->dmax, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMemcpyAsync(pk_cm, pk, sizeof(double) * count * rj->nm, cudaMemcpyHostToDevice, stream()));
+  rj_state_scatter_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream()>>>(s, first, count, th_cm, pk_cm);
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  AMX_CUDA(cudaMemcpyAsync(s.lp + first, lp, sizeof(double) * count, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMemcpyAsync(s.k + first, k, sizeof(int) * count, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMemcpyAsync(s.nreinit + first, nreinit, sizeof(int) * count, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaMemcpyAsync(s.pkllim + first, pkllim, sizeof(double) * count, cudaMemcpyHostToDevice, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
   rj->sweep_i = sweep_i;
   return AMX_OK;
 }
@@ -750,19 +774,24 @@ int amx_rj_get_state(const amx_rj *rj, long first, long count, double *theta, do
                      int *nreinit, double *pkllim, unsigned long long *sweep_i) {
   if (!rj || first < 0 || count < 1 || first + count > rj->C) return fail(AMX_EINVAL, "amx_rj_get_state: range");
   const RjState &s = rj->st;
+  amx_rj *w = const_cast<amx_rj *>(rj);
+  if (theta || pk) {
+    const long need = count * (rj->dmax + rj->nm);
+    if (need > w->stage_cap) {
+      cudaFree(w->stage_dev);
+      w->stage_dev = nullptr;
+      AMX_CUDA(cudaMalloc(&w->stage_dev, sizeof(double) * need));
+      w->stage_cap = need;
+    }
+    double *th_cm = w->stage_dev, *pk_cm = w->stage_dev + count * rj->dmax;
+    rj_state_gather_kernel<<<(unsigned)((count + 255) / 256), 256, 0, stream()>>>(s, first, count, theta ? th_cm : nullptr,
+                                                                                  pk ? pk_cm : nullptr);
+    count_launch();
+    AMX_CUDA(cudaGetLastError());
+    if (theta) AMX_CUDA(cudaMemcpyAsync(theta, th_cm, sizeof(double) * count * rj->dmax, cudaMemcpyDeviceToHost, stream()));
+    if (pk) AMX_CUDA(cudaMemcpyAsync(pk, pk_cm, sizeof(double) * count * rj->nm, cudaMemcpyDeviceToHost, stream()));
+  }
   AMX_CUDA(cudaStreamSynchronize(stream()));
-  if (theta)
-    for (int i = 0; i < rj->dmax; i++) {
-      std::vector<double> col(count);
-      AMX_CUDA(cudaMemcpy(col.data(), s.theta + (size_t)i * rj->C + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
-      for (long c = 0; c < count; c++) theta[c * rj->dmax + i] = col[c];
-    }
-  if (pk)
-    for (int j = 0; j < rj->nm; j++) {
-      std::vector<double> col(count);
-      AMX_CUDA(cudaMemcpy(col.data(), s.pk + (size_t)j * rj->C + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
-      for (long c = 0; c < count; c++) pk[c * rj->nm + j] = col[c];
-    }
   if (lp) AMX_CUDA(cudaMemcpy(lp, s.lp + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
   if (k) AMX_CUDA(cudaMemcpy(k, s.k + first, sizeof(int) * count, cudaMemcpyDeviceToHost));
   if (nreinit) AMX_CUDA(cudaMemcpy(nreinit, s.nreinit + first, sizeof(int) * count, cudaMemcpyDeviceToHost));

@@ -233,40 +233,46 @@ def main():
     if rank == 0:
         ach = float(st["flops"]) / (st["kernel_ms"] * 1e-3)  # this rank's dominant kernel, per-launch average
         roof_rj = {"bound": "fp64", "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                   "frac": ach / fp64_peak, "traffic": None,
+                   "frac": ach / fp64_peak,
+                   # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 chains (state load/store
+                   # only; independent of the number of sweeps): profiles/r01/ncu_rj_r01c.txt
+                   "traffic": 78.3e6 * (C / float(1 << 20)),
+                   "fp64_pipe_active_pct_ncu": 26.6,
                    "kernel": "rj_sweep_kernel", "launch_ms": st["kernel_ms"] / args.steps,
                    "flops_per_sweep": float(st["flops"]) / (C * S * args.steps),
                    "peak_source": "measured live with amx_measure_fp64_peak (dependent-free DFMA loop); "
                                   "MEASURED_PEAKS.json has no fp64 entry (SURVEY.md 8d)",
                    "note": "algorithmic F_RJ flops of SURVEY.md 8d (exp/log/sqrt/sincos count as 1 flop each)"}
 
-    # end-to-end through the C-ABI with host buffers: H2D of the inputs, the sweeps, D2H of the result
+    # end-to-end through the C-ABI with HOST buffers: every step uploads all chain states from pinned host
+    # memory, runs the sweeps, and reads all chain states, the histogram and the counters back
     e2e = None
     if True:
         e2e_steps = max(2, min(args.steps, 5))
-        init_pin = torch.from_numpy(init.copy()).pin_memory()
+        fin = pop.get_state()
+        pinned = {}
+        for key in ("theta", "pk", "lp", "k", "nreinit", "pkllim"):
+            tns = torch.from_numpy(np.ascontiguousarray(fin[key])).pin_memory()
+            pinned[key] = tns.numpy()
+            pinned["_t_" + key] = tns  # keep the pinned tensors alive
+        sweep_i = fin["sweep_i"]
+        h2d = int(sum(pinned[q].nbytes for q in ("theta", "pk", "lp", "k", "nreinit", "pkllim")))
+        pop.collect(reset=True)
         barrier()
         t0 = time.perf_counter()
-        d2h = 0
         for s in range(e2e_steps):
-            P2 = amx.Proposal(mix)                       # H2D: proposal blob
-            T2 = amx.Target(wl["target"])                # H2D: plug-in parameters
-            pop2 = amx.RjPopulation(P2, T2, C, init_pin.numpy(), seed=7 + s)  # H2D: start vectors
-            pop2.set_chain_base(shard.weak_range(C, rank)[0])
-            pop2.init_chains()
-            pop2.sweeps(S)
-            v2, st2 = pop2.collect()                     # D2H: histogram + counters
-            fin = pop2.get_state()                       # D2H: every chain's final state (the posterior sample)
-            d2h = sum(a.nbytes for a in fin.values() if hasattr(a, "nbytes")) + v2.nbytes + 72
-            pop2.close(); T2.close(); P2.close()
+            pop.set_state_arrays(pinned, sweep_i)        # H2D: all chain states
+            pop.sweeps(S)
+            v2, st2 = pop.collect(reset=True)             # D2H: histogram + counters
+            out = pop.get_state(out=pinned)               # D2H: all chain states (the posterior sample)
+            sweep_i = out["sweep_i"]
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         shard.allreduce_max_(te)
-        h2d = int(P.mix["wt"].nbytes + P.mix["mean"].nbytes + P.mix["tri"].nbytes + P.mix["sig"].nbytes + init.nbytes + 2048)
         e2e = {"value": float(world) * C * S * e2e_steps / float(te.cpu()[0]), "unit": "chain-sweeps/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-               "what": "per step: create proposal + plug-in + population from host arrays, chain start, "
-                       f"{S} sweeps, read back histogram, counters and all {C} final chain states"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d + 8 * nm + 72,
+               "what": f"per step through the C-ABI with pinned host buffers: amx_rj_set_state of all {C} chains, "
+                       f"{S} sweeps, amx_rj_collect, amx_rj_get_state of all chains"}
     pop.close()
     del flush
 
@@ -305,7 +311,10 @@ def main():
                                      f"({its} outer iterations), 6-component synthetic mixture (seed 2025); "
                                      "inputs (80 MB) + density cache (240 MB) exceed L2, no flush needed"},
               "roofline": {"bound": "hbm", "achieved": alg_bytes / t_fit / 1e9, "peak": hbm, "unit": "GB/s",
-                           "frac": alg_bytes / t_fit / 1e9 / hbm, "traffic": None,
+                           "frac": alg_bytes / t_fit / 1e9 / hbm,
+                           # ncu: 28.35 GB (read+write) for 74 component steps + start-up at n=1e6, d=10
+                           # (profiles/r01/ncu_em_r01c.txt) -> 0.383 GB per component step, scaled to this launch
+                           "traffic": 0.383e9 * steps_ * (n / 1e6) * ((2 * d + L + 3) / 53.0),
                            "kernel": "em_fit_kernel", "launch_ms": 1e3 * t_fit,
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                            "note": "algorithmic bytes = 8 d per sample-component-step (SURVEY.md 8d)",
