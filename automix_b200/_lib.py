@@ -46,7 +46,7 @@ EXPORTS = [
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
     "amx_rj_set_tape", "amx_rj_set_chain_base", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
     "amx_rj_collect", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_em_fit", "amx_em_fit_dev",
-    "amx_em_draw_init", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
+    "amx_em_draw_init", "amx_em_fit_multi", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
 ]
 
 
@@ -98,6 +98,8 @@ def lib():
                                  _ip, _dp, _dp, _dp, _ip, _dp, C.POINTER(EmResult)]
         L.amx_em_fit_dev.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _ip,
                                      _dp, _dp, _ip, C.POINTER(EmResult)]
+        L.amx_em_fit_multi.argtypes = [C.c_int, _ip, C.c_int, C.c_long, _dp, C.c_int, C.c_int, _ip, _dp, _dp, _dp, _ip,
+                                       _dp, _dp, _ip, _dp, _dp, _dp, _ip, _dp, C.POINTER(EmResult)]
         L.amx_em_draw_init.restype = C.c_long
         L.amx_em_draw_init.argtypes = [C.c_long, C.c_int, _dp, C.c_long, _ip]
         L.amx_autorj_fit.argtypes = [C.c_int, C.c_long, _dp, _dp, _dp, _dp]
@@ -340,8 +342,9 @@ def em_draw_init(n, Lmax, uniforms):
     return idx, int(used)
 
 
-def em_fit(x, init_idx, Lmax=30, maxit=5000, want_state=False, x_dev_ptr=None):
-    """Figueiredo-Jain EM fit on the GPU.  x: (n,d) host array, or pass x_dev_ptr (+ shape via x)."""
+def em_fit(x, init_idx, Lmax=30, maxit=5000, want_state=False, x_dev_ptr=None, devices=None):
+    """Figueiredo-Jain EM fit on the GPU.  x: (n,d) host array, or pass x_dev_ptr (+ shape via x).
+    devices: list of CUDA ordinals to shard the samples over (amx_em_fit_multi)."""
     L = lib()
     n, d = x.shape
     t = d * (d + 1) // 2
@@ -364,9 +367,15 @@ def em_fit(x, init_idx, Lmax=30, maxit=5000, want_state=False, x_dev_ptr=None):
         if want_state:
             st = dict(cur_wt=np.zeros(Lmax), cur_mean=np.zeros((Lmax, d)), cur_tri=np.zeros((Lmax, t)),
                       cur_L=np.zeros(1, np.int32), cur_w=np.zeros((n, Lmax)))
-        check(L.amx_em_fit(d, n, _d(x), Lmax, maxit, _i(init_idx), _d(wt), _d(mean), _d(tri), _i(trL), _d(trll),
-                           _d(trc), _i(tra), _d(st.get("cur_wt")), _d(st.get("cur_mean")), _d(st.get("cur_tri")),
-                           _i(st.get("cur_L")), _d(st.get("cur_w")), C.byref(res)))
+        if devices is not None:
+            dv = i32(devices)
+            check(L.amx_em_fit_multi(len(dv), _i(dv), d, n, _d(x), Lmax, maxit, _i(init_idx), _d(wt), _d(mean), _d(tri),
+                                     _i(trL), _d(trll), _d(trc), _i(tra), _d(st.get("cur_wt")), _d(st.get("cur_mean")),
+                                     _d(st.get("cur_tri")), _i(st.get("cur_L")), _d(st.get("cur_w")), C.byref(res)))
+        else:
+            check(L.amx_em_fit(d, n, _d(x), Lmax, maxit, _i(init_idx), _d(wt), _d(mean), _d(tri), _i(trL), _d(trll),
+                               _d(trc), _i(tra), _d(st.get("cur_wt")), _d(st.get("cur_mean")), _d(st.get("cur_tri")),
+                               _i(st.get("cur_L")), _d(st.get("cur_w")), C.byref(res)))
     Lb, it = res.L, res.iters
     out = dict(L=Lb, iters=it, lam=wt[:Lb].copy(), mu=mean[:Lb].copy(), B=tri[:Lb].copy(), trace_L=trL[:it].copy(),
                trace_loglik=trll[:it].copy(), trace_cost=trc[:it].copy(), trace_ann=tra[:it].copy(),

@@ -73,15 +73,40 @@ struct EmCtrl {
   double best_B[kEmLmax][kEmTriMax];
 };
 
+constexpr int kEmMaxDev = 8;
+
+// What every CTA needs to know after a barrier; the leader pushes a copy to every GPU (peer stores), so the
+// reload that follows the barrier reads local memory only.
+struct EmPublic {
+  int pass, L, c, next;
+  int slot[kEmLmax];
+  double lam[kEmLmax];
+  double rec[kEmRecMax];
+};
+
+// The per-GPU pieces of a sample-sharded fit.  All pointers are valid on every participating GPU (peer
+// access over NVLink); only the leader touches another GPU's memory.
+struct EmDev {
+  double *part;      // [NV][grid] value-major per-CTA partials of the pass in flight
+  double *devrow;    // [NV] this GPU's partials reduced by its last-arriving CTA
+  unsigned *flags;   // [grid * 8] per-CTA release flags
+  unsigned *arrive;  // arrival counter of this GPU's CTAs
+  EmPublic *pub;     // local mirror of the public control state
+  int grid;
+};
+
 struct EmArgs {
+  int ndev, rank;        // GPUs sharing the fit, and which one this launch runs on
+  long n_total;          // samples over all GPUs (n below is this GPU's shard)
+  const double *init_rows;  // [Lmax][d] the data rows that start the components (on GPU 0)
+  EmDev dev[kEmMaxDev];
   int d, Lmax, maxit;
   int use_tma;  // 1: tile rows by cp.async.bulk + mbarrier; 0: coalesced per-thread loads into the tile
   int nbuf;  // tile buffers per CTA: 2 = fetch of tile k+1 overlaps tile k, 1 = more resident CTAs
   long n, npad;
   const double *x;  // n x d row-major (device)
-  double *xT, *E, *wnxt, *part;
-  unsigned *flags;  // [grid * 8] per-CTA release flags of the grid barrier
-  EmCtrl *ctrl;
+  double *xT, *E, *wnxt;
+  EmCtrl *ctrl;  // the sequential state of the algorithm (on GPU 0)
   const int *init_idx;  // device
   int *trace_L, *trace_ann;
   double *trace_loglik, *trace_cost;
@@ -93,41 +118,100 @@ __device__ __forceinline__ T ld_cg(const T *p) {
   return __ldcg(p);
 }
 
-// ---- grid barrier with a leader ---------------------------------------------------------------------
-// Every CTA arrives; the last one returns true and must call barrier_release() when it has
-// finished its serial section; the others wait inside.  Counters only grow, so no reset races.
-__device__ __forceinline__ bool barrier_arrive(EmCtrl *ctrl, unsigned &epoch) {
+// ---- barrier with a leader, across the CTAs of one GPU and across GPUs ---------------------------------
+// Every CTA arrives at its GPU's counter.  The last CTA of a GPU reduces that GPU's partials into its
+// `devrow` and arrives at the global counter (a system-scope atomic on GPU 0's memory, over NVLink when
+// remote).  The last GPU's CTA is the leader: it sums the per-GPU rows through peer loads in GPU order,
+// runs the sequential section, pushes the public state and the release flags to every GPU with peer stores.
+// Counters only grow, so there are no reset races; waiters poll a flag in their own GPU's memory.
+__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot, double *s_chunk);
+
+__device__ __forceinline__ int barrier_arrive(const EmArgs &a, unsigned &epoch, int nv, double *s_tot, double *s_chunk) {
   __shared__ int s_last;
+  const EmDev &me = a.dev[a.rank];
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned t = atomicAdd(&ctrl->arrive, 1u);
-    s_last = (t == gridDim.x * (epoch + 1u) - 1u) ? 1 : 0;
+    const unsigned t = atomicAdd(me.arrive, 1u);
+    s_last = (t == (unsigned)me.grid * (epoch + 1u) - 1u) ? 1 : 0;
     if (s_last) __threadfence();
   }
   __syncthreads();
-  return s_last != 0;
-}
-// Release: the leader's threads write one flag per CTA (32-byte stride: every waiter polls its own sector,
-// so there is no hot L2 line -- 592 CTAs polling one address saturate its slice and slow the leader down).
-__device__ __forceinline__ void barrier_release(unsigned *flags, unsigned &epoch) {
+  if (!s_last) return 0;
+  if (nv > 0) leader_reduce(me.part, nv, s_tot, s_chunk);  // this GPU's CTAs, coalesced, fixed order
+  if (a.ndev == 1) return 2;
+  for (int q = threadIdx.x; q < nv; q += blockDim.x) __stcg(me.devrow + q, s_tot[q]);
+  __threadfence_system();
   __syncthreads();
-  __threadfence();
-  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) __stcg(flags + 8u * b, epoch + 1u);
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd_system(&a.ctrl->arrive, 1u);
+    s_last = (t == (unsigned)a.ndev * (epoch + 1u) - 1u) ? 1 : 0;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (!s_last) return 1;
+  for (int q = threadIdx.x; q < nv; q += blockDim.x) {  // the per-GPU rows, in GPU order
+    double t = 0.0;
+    for (int g = 0; g < a.ndev; g++) t += ld_cg(a.dev[g].devrow + q);
+    s_tot[q] = t;
+  }
+  __syncthreads();
+  return 2;
+}
+
+// Leader: publish the state to every GPU, then release every CTA.
+__device__ __forceinline__ void barrier_release(const EmArgs &a, int d, unsigned &epoch) {
+  const EmCtrl *c = a.ctrl;
+  if (a.ndev > 1) __threadfence_system();
+  else __threadfence();
+  __syncthreads();
+  const int reclen = AMX_REC_HEAD + 2 * d + d * (d + 1) / 2;
+  for (int g = 0; g < a.ndev; g++) {
+    EmPublic *p = a.dev[g].pub;
+    if (threadIdx.x == 0) {
+      __stcg(&p->pass, ld_cg(&c->pass));
+      __stcg(&p->L, ld_cg(&c->L));
+      __stcg(&p->c, ld_cg(&c->c));
+      __stcg(&p->next, ld_cg(&c->next));
+    }
+    if (threadIdx.x < kEmLmax) {
+      __stcg(&p->slot[threadIdx.x], ld_cg(&c->slot[threadIdx.x]));
+      __stcg(&p->lam[threadIdx.x], ld_cg(&c->lam[threadIdx.x]));
+    }
+    for (int q = threadIdx.x; q < reclen; q += blockDim.x) __stcg(&p->rec[q], ld_cg(&c->rec[q]));
+  }
+  if (a.ndev > 1) __threadfence_system();
+  else __threadfence();
+  __syncthreads();
+  for (int g = 0; g < a.ndev; g++)
+    for (unsigned b = threadIdx.x; b < (unsigned)a.dev[g].grid; b += blockDim.x) __stcg(a.dev[g].flags + 8u * b, epoch + 1u);
   epoch++;
 }
-__device__ __forceinline__ void barrier_wait(unsigned *flags, unsigned &epoch) {
+
+// Waiters poll their own flag (32-byte stride: no hot L2 line).  A watchdog turns a lost partner into an
+// error instead of a hang.
+__device__ __forceinline__ bool barrier_wait(const EmArgs &a, unsigned &epoch) {
+  __shared__ int s_ok;
   if (threadIdx.x == 0) {
-    const unsigned *f = flags + 8u * blockIdx.x;
+    const unsigned *f = a.dev[a.rank].flags + 8u * blockIdx.x;
     unsigned ns = 64;
+    const long long t0 = clock64();
+    int ok = 1;
     while (ld_cg(f) <= epoch) {
       __nanosleep(ns);
       if (ns < 512) ns *= 2;
+      if (clock64() - t0 > 40000000000LL) {  // ~20 s at 2 GHz
+        ok = 0;
+        break;
+      }
     }
-    __threadfence();
+    if (a.ndev > 1) __threadfence_system();
+    else __threadfence();
+    s_ok = ok;
   }
   epoch++;
   __syncthreads();
+  return s_ok != 0;
 }
 
 // ---- CTA-level reduction of NV per-thread values into part[blockIdx][*] -----------------------------
@@ -333,7 +417,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
     // :700-723 common isotropic start; s_tot = [sum x_j (d) | sum x_j^2 (d)]
     if (t == 0) {
       double s2 = 0.0;
-      const double len = (double)a.n;
+      const double len = (double)a.n_total;
       for (int j = 0; j < d; j++) s2 += (s_tot[d + j] - s_tot[j] * s_tot[j] / len) / len;
       s2 /= (10.0 * d);
       c->s2 = s2;
@@ -346,7 +430,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
     __syncthreads();
     for (int q = t; q < a.Lmax * d; q += blockDim.x) {
       const int l = q / d, j = q % d;
-      c->mu[l][j] = a.x[(size_t)a.init_idx[l] * d + j];
+      c->mu[l][j] = ld_cg(a.init_rows + (size_t)l * d + j);
     }
     for (int q = t; q < a.Lmax * tri; q += blockDim.x) c->B[q / tri][q % tri] = 0.0;
     __syncthreads();
@@ -416,7 +500,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
     }
     __syncthreads();
     if (S.forced_pending) {  // uniform: the cost after the forced annihilation
-      leader_cost<DMAX>(S, a.n, nparams);
+      leader_cost<DMAX>(S, a.n_total, nparams);
       if (t == 0) S.forced_pending = 0;
       __syncthreads();
     }
@@ -435,7 +519,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
           }
           S.lam[cc] = wkeep / tot;
           S.comp_steps++;
-          S.flops += (double)a.n * (2.0 * d * d + 8.0 * d + 4.0 * S.L + 7.0);
+          S.flops += (double)a.n_total * (2.0 * d * d + 8.0 * d + 4.0 * S.L + 7.0);
         }
         __syncthreads();
         leader_renorm<DMAX>(S);
@@ -460,7 +544,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
           }
         }
       } else if (act == kActEndSweep) {
-        leader_cost<DMAX>(S, a.n, nparams);
+        leader_cost<DMAX>(S, a.n_total, nparams);
         if (t == 0) {
           if (S.iters == 1) S.cost_prev = S.cost;
           S.savebest = (S.iters == 1 || S.cost < S.cost_best) ? 1 : 0;  // :881-893
@@ -620,7 +704,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
   const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tile_doubles = (d + a.Lmax + 1) * kEmTS;  // two such buffers: fetch of tile k+1 overlaps tile k
-  double *part_col = a.part + blockIdx.x;  // value q of this CTA lives at part_col[q * gridDim.x]
+  double *part_col = a.dev[a.rank].part + blockIdx.x;  // value q of this CTA lives at part_col[q * gridDim.x]
   const size_t pstride = gridDim.x;
   unsigned epoch = 0;
   uint32_t tma_phase[4] = {0u, 0u, 0u, 0u};
@@ -960,45 +1044,49 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
 
     // ------------------------------------------------------------------ barrier + leader
     const long long tk1 = clock64();
-    if (barrier_arrive(ctrl, epoch)) {
-      const long long tl0 = clock64();
-      if (nv > 0) leader_reduce(a.part, nv, s_tot, s_chunk);
+    const int role = barrier_arrive(a, epoch, nv, s_tot, s_chunk);
+    bool alive = true;
+    if (role == 2) {
       const long long tl1 = clock64();
       em_leader_block<DMAX>(ctrl, a, pass, s_tot, s_lead);
       const long long tl2 = clock64();
-      barrier_release(a.flags, epoch);
+      barrier_release(a, d, epoch);
       __syncthreads();
-      if (threadIdx.x == 0) {
-        atomicAdd((unsigned long long *)&ctrl->dbg[2], (unsigned long long)(tl1 - tl0));
+      if (threadIdx.x == 0 && a.rank == 0) {
         atomicAdd((unsigned long long *)&ctrl->dbg[3], (unsigned long long)(tl2 - tl1));
-        atomicAdd((unsigned long long *)&ctrl->dbg[1], (unsigned long long)(tl0 - tk1));
+        atomicAdd((unsigned long long *)&ctrl->dbg[1], (unsigned long long)(tl1 - tk1));
       }
     } else {
-      barrier_wait(a.flags, epoch);
-      if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&ctrl->dbg[4], (unsigned long long)(clock64() - tk1));
+      alive = barrier_wait(a, epoch);
+      if (threadIdx.x == 0 && blockIdx.x == 0 && a.rank == 0) atomicAdd((unsigned long long *)&ctrl->dbg[4], (unsigned long long)(clock64() - tk1));
     }
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (!alive) {  // a partner never arrived: report and leave instead of hanging
+      if (threadIdx.x == 0) atomicExch(&ctrl->status, AMX_ECUDA);
+      return;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0 && a.rank == 0) {
       atomicAdd((unsigned long long *)&ctrl->dbg[0], (unsigned long long)(tk1 - tk0));
       if (pass == kPassScatter) atomicAdd((unsigned long long *)&ctrl->dbg[6], (unsigned long long)(tk1 - tk0));
       if (pass == kPassDensRefresh || pass == kPassRefresh) atomicAdd((unsigned long long *)&ctrl->dbg[7], (unsigned long long)(tk1 - tk0));
     }
     const long long tk2 = clock64();
     // ------------------------------------------------------------------ reload the control state
+    const EmPublic *pub = a.dev[a.rank].pub;  // this GPU's mirror, written by the leader before the release
     if (threadIdx.x == 0) {
-      s_pass = ld_cg(&ctrl->pass);
-      s_L = ld_cg(&ctrl->L);
-      s_c = ld_cg(&ctrl->c);
-      s_next = ld_cg(&ctrl->next);
+      s_pass = ld_cg(&pub->pass);
+      s_L = ld_cg(&pub->L);
+      s_c = ld_cg(&pub->c);
+      s_next = ld_cg(&pub->next);
     }
     if (threadIdx.x < kEmLmax) {
-      s_lam[threadIdx.x] = ld_cg(&ctrl->lam[threadIdx.x]);
-      s_slot[threadIdx.x] = ld_cg(&ctrl->slot[threadIdx.x]);
+      s_lam[threadIdx.x] = ld_cg(&pub->lam[threadIdx.x]);
+      s_slot[threadIdx.x] = ld_cg(&pub->slot[threadIdx.x]);
     }
     const int reclen = AMX_REC_HEAD + 2 * d + d * (d + 1) / 2;
-    for (int q = threadIdx.x; q < reclen; q += blockDim.x) s_rec[q] = ld_cg(&ctrl->rec[q]);
+    for (int q = threadIdx.x; q < reclen; q += blockDim.x) s_rec[q] = ld_cg(&pub->rec[q]);
     __syncthreads();
     pass = s_pass;
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&ctrl->dbg[5], (unsigned long long)(clock64() - tk2));
+    if (threadIdx.x == 0 && blockIdx.x == 0 && a.rank == 0) atomicAdd((unsigned long long *)&ctrl->dbg[5], (unsigned long long)(clock64() - tk2));
     if (pass == kPassStop) break;
   }
 
@@ -1071,35 +1159,273 @@ __global__ void __launch_bounds__(256) autorj_generic_kernel(int d, long n, cons
 using namespace amx;
 
 template <int DMAX>
-static int em_launch(EmArgs &a, int sms, float *ms) {
-  const char *nb = getenv("AMX_EM_NBUF"), *tm = getenv("AMX_EM_TMA");
-  a.nbuf = nb ? (atoi(nb) == 2 ? 2 : 1) : 1;
-  a.use_tma = tm ? (atoi(tm) != 0) : 1;  // measured on B200 (n=1e6, d=10, L=30): TMA 183 us/step, plain loads 244
-  if (!a.use_tma) a.nbuf = 1;
-  const size_t smem = a.nbuf * sizeof(double) * (size_t)(a.d + a.Lmax + 1) * kEmTS;
+static int em_occupancy(size_t smem, int *per_sm) {
   AMX_CUDA(cudaFuncSetAttribute(em_fit_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  AMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, em_fit_kernel<DMAX>, kEmThreads, smem));
-  if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM (%zu B of shared memory)", smem);
-  long want = a.npad / kEmThreads;  // tiles
-  long cap = (long)sms * per_sm;
-  unsigned grid = (unsigned)(want < cap ? want : cap);
-  if (grid < 1) grid = 1;
-  AMX_CUDA(cudaMalloc(&a.part, sizeof(double) * (size_t)grid * kEmNV));
-  AMX_CUDA(cudaMalloc(&a.flags, sizeof(unsigned) * 8 * (size_t)grid));
-  AMX_CUDA(cudaMemsetAsync(a.flags, 0, sizeof(unsigned) * 8 * (size_t)grid, stream()));
+  AMX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, em_fit_kernel<DMAX>, kEmThreads, smem));
+  return AMX_OK;
+}
+template <int DMAX>
+static int em_launch_one(EmArgs &a, unsigned grid, size_t smem, cudaStream_t st) {
   void *args[] = {&a};
+  AMX_CUDA(cudaLaunchCooperativeKernel((void *)em_fit_kernel<DMAX>, dim3(grid), dim3(kEmThreads), args, smem, st));
+  count_launch();
+  return AMX_OK;
+}
+static int em_occupancy_d(int d, size_t smem, int *per_sm) {
+  if (d <= 4) return em_occupancy<4>(smem, per_sm);
+  if (d <= 8) return em_occupancy<8>(smem, per_sm);
+  if (d <= 12) return em_occupancy<12>(smem, per_sm);
+  if (d <= 20) return em_occupancy<20>(smem, per_sm);
+  return em_occupancy<32>(smem, per_sm);
+}
+static int em_launch_d(int d, EmArgs &a, unsigned grid, size_t smem, cudaStream_t st) {
+  if (d <= 4) return em_launch_one<4>(a, grid, smem, st);
+  if (d <= 8) return em_launch_one<8>(a, grid, smem, st);
+  if (d <= 12) return em_launch_one<12>(a, grid, smem, st);
+  if (d <= 20) return em_launch_one<20>(a, grid, smem, st);
+  return em_launch_one<32>(a, grid, smem, st);
+}
+
+// One fit over ndev GPUs (ndev = 1: the ordinary fit).  The samples are split into contiguous shards, one
+// per GPU; every GPU runs the same persistent kernel on its shard and they meet at the cross-GPU barrier of
+// the kernel, exchanging only the per-pass partial sums (<= 2 KB per GPU) through peer memory.
+// x_host: n x d row-major host samples, or NULL with x_dev0 = device samples (ndev must be 1).
+static int em_fit_general(int ndev, const int *devices, int d, long n, const double *x_host, const double *x_dev0,
+                          int Lmax, int maxit, const int *init_idx, double *wt, double *mean, double *tri, int *trace_L,
+                          double *trace_loglik, double *trace_cost, int *trace_ann, double *cur_wt, double *cur_mean,
+                          double *cur_tri, int *cur_L, double *cur_w, amx_em_result *res) {
+  if (d < 1 || d > kEmDmax || Lmax < 1 || Lmax > kEmLmax || n < 1 || maxit < 0 || !init_idx || !wt || !mean || !tri)
+    return fail(AMX_EINVAL, "amx_em_fit: need 1<=d<=%d, 1<=Lmax<=%d, n>=1, maxit>=0 (got d=%d Lmax=%d n=%ld maxit=%d)",
+                kEmDmax, kEmLmax, d, Lmax, n, maxit);
+  if (n < Lmax) return fail(AMX_EINVAL, "amx_em_fit: fewer samples (%ld) than start components (%d)", n, Lmax);
+  if (ndev < 1 || ndev > kEmMaxDev || (ndev > 1 && !x_host)) return fail(AMX_EINVAL, "amx_em_fit: bad device list");
+  if (n < (long)ndev * kEmThreads) ndev = 1;  // nothing to share
+  for (int l = 0; l < Lmax; l++) {
+    if (init_idx[l] < 0 || init_idx[l] >= n) return fail(AMX_EINVAL, "amx_em_fit: init_idx[%d]=%d out of range", l, init_idx[l]);
+    for (int m = 0; m < l; m++)
+      if (init_idx[m] == init_idx[l]) return fail(AMX_EINVAL, "amx_em_fit: start rows must be distinct");
+  }
+  int home = 0;
+  AMX_CUDA(cudaGetDevice(&home));
+  int devs[kEmMaxDev];
+  for (int g = 0; g < ndev; g++) devs[g] = devices ? devices[g] : home;
+  int sms = 0, coop = 0;
+  AMX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devs[0]));
+  AMX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, devs[0]));
+  if (!coop) return fail(AMX_ECUDA, "device lacks cooperative launch");
+  const int tlen = d * (d + 1) / 2, cap = maxit + 1;
+  const char *nb = getenv("AMX_EM_NBUF"), *tm = getenv("AMX_EM_TMA");
+  const int use_tma = tm ? (atoi(tm) != 0) : 1;  // measured on B200 (n=1e6, d=10, L=30): TMA 183 us/step, plain loads 244
+  const int nbuf = (use_tma && nb && atoi(nb) == 2) ? 2 : 1;
+  const size_t smem = nbuf * sizeof(double) * (size_t)(d + Lmax + 1) * kEmTS;
+
+  EmArgs A[kEmMaxDev];
+  cudaStream_t st[kEmMaxDev];
+  int *idx_dev = nullptr;
+  double *init_rows = nullptr;
+  EmCtrl *ctrl = nullptr;
+  int *tr_L = nullptr, *tr_ann = nullptr;
+  double *tr_ll = nullptr, *tr_cost = nullptr;
+  long off[kEmMaxDev + 1];
+  off[0] = 0;
+  for (int g = 0; g < ndev; g++) off[g + 1] = off[g] + n / ndev + (g < n % ndev ? 1 : 0);
+  memset(A, 0, sizeof(A));
+  int rc = AMX_OK;
+
+  // peer access between all participants
+  if (ndev > 1)
+    for (int g = 0; g < ndev; g++) {
+      AMX_CUDA(cudaSetDevice(devs[g]));
+      for (int h = 0; h < ndev; h++)
+        if (h != g) {
+          int can = 0;
+          AMX_CUDA(cudaDeviceCanAccessPeer(&can, devs[g], devs[h]));
+          if (!can) {
+            cudaSetDevice(home);
+            return fail(AMX_ECUDA, "GPU %d cannot access GPU %d's memory", devs[g], devs[h]);
+          }
+          cudaError_t e = cudaDeviceEnablePeerAccess(devs[h], 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            cudaSetDevice(home);
+            return fail(AMX_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+          }
+          cudaGetLastError();
+        }
+    }
+
+  // GPU 0: the control block, the traces and the start rows
+  AMX_CUDA(cudaSetDevice(devs[0]));
+  AMX_CUDA(cudaMalloc(&ctrl, sizeof(EmCtrl)));
+  AMX_CUDA(cudaMemset(ctrl, 0, sizeof(EmCtrl)));
+  AMX_CUDA(cudaMalloc(&init_rows, sizeof(double) * (size_t)Lmax * d));
+  AMX_CUDA(cudaMalloc(&tr_L, sizeof(int) * cap));
+  AMX_CUDA(cudaMalloc(&tr_ann, sizeof(int) * cap));
+  AMX_CUDA(cudaMalloc(&tr_ll, sizeof(double) * cap));
+  AMX_CUDA(cudaMalloc(&tr_cost, sizeof(double) * cap));
+  for (int l = 0; l < Lmax; l++) {
+    if (x_host)
+      AMX_CUDA(cudaMemcpy(init_rows + (size_t)l * d, x_host + (size_t)init_idx[l] * d, sizeof(double) * d, cudaMemcpyHostToDevice));
+    else
+      AMX_CUDA(cudaMemcpy(init_rows + (size_t)l * d, x_dev0 + (size_t)init_idx[l] * d, sizeof(double) * d, cudaMemcpyDeviceToDevice));
+  }
+  (void)idx_dev;
+
+  // per-GPU shards
+  for (int g = 0; g < ndev; g++) {
+    AMX_CUDA(cudaSetDevice(devs[g]));
+    EmArgs &a = A[g];
+    a.ndev = ndev;
+    a.rank = g;
+    a.n_total = n;
+    a.init_rows = init_rows;
+    a.d = d;
+    a.Lmax = Lmax;
+    a.maxit = maxit;
+    a.use_tma = use_tma;
+    a.nbuf = nbuf;
+    a.n = off[g + 1] - off[g];
+    a.npad = (a.n + kEmThreads - 1) / kEmThreads * kEmThreads;  // whole tiles; the padding is zero and carries no weight
+    a.ctrl = ctrl;
+    a.trace_L = tr_L;
+    a.trace_ann = tr_ann;
+    a.trace_loglik = tr_ll;
+    a.trace_cost = tr_cost;
+    if (g == 0 && ndev == 1) st[g] = stream();
+    else AMX_CUDA(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
+    if (x_host) {
+      double *xs = nullptr;
+      AMX_CUDA(cudaMalloc(&xs, sizeof(double) * (size_t)a.n * d));
+      AMX_CUDA(cudaMemcpyAsync(xs, x_host + (size_t)off[g] * d, sizeof(double) * (size_t)a.n * d, cudaMemcpyHostToDevice, st[g]));
+      a.x = xs;
+    } else {
+      a.x = x_dev0;
+    }
+    AMX_CUDA(cudaMalloc(&a.xT, sizeof(double) * (size_t)d * a.npad));
+    AMX_CUDA(cudaMalloc(&a.E, sizeof(double) * (size_t)Lmax * a.npad));
+    AMX_CUDA(cudaMalloc(&a.wnxt, sizeof(double) * (size_t)a.npad));
+    AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, st[g]));
+    AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, st[g]));
+    AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, st[g]));
+    if (cur_w) AMX_CUDA(cudaMalloc(&a.w_out, sizeof(double) * (size_t)a.n * Lmax));
+    int per_sm = 0;
+    if ((rc = em_occupancy_d(d, smem, &per_sm))) return rc;
+    if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM (%zu B of shared memory)", smem);
+    long want = a.npad / kEmThreads, capb = (long)sms * per_sm;
+    unsigned grid = (unsigned)(want < capb ? want : capb);
+    EmDev dv;
+    memset(&dv, 0, sizeof(dv));
+    dv.grid = (int)grid;
+    AMX_CUDA(cudaMalloc(&dv.part, sizeof(double) * (size_t)grid * kEmNV));
+    AMX_CUDA(cudaMalloc(&dv.devrow, sizeof(double) * kEmNV));
+    AMX_CUDA(cudaMalloc(&dv.flags, sizeof(unsigned) * 8 * (size_t)grid));
+    AMX_CUDA(cudaMalloc(&dv.arrive, sizeof(unsigned) * 8));
+    AMX_CUDA(cudaMalloc(&dv.pub, sizeof(EmPublic)));
+    AMX_CUDA(cudaMemsetAsync(dv.flags, 0, sizeof(unsigned) * 8 * (size_t)grid, st[g]));
+    AMX_CUDA(cudaMemsetAsync(dv.arrive, 0, sizeof(unsigned) * 8, st[g]));
+    AMX_CUDA(cudaMemsetAsync(dv.pub, 0, sizeof(EmPublic), st[g]));
+    for (int h = 0; h < ndev; h++) A[h].dev[g] = dv;
+  }
+  for (int g = 0; g < ndev; g++) {  // everything above must have landed before any kernel starts
+    AMX_CUDA(cudaSetDevice(devs[g]));
+    AMX_CUDA(cudaStreamSynchronize(st[g]));
+  }
+
+  // launch: one persistent cooperative kernel per GPU; they wait for one another inside
   cudaEvent_t e0, e1;
+  AMX_CUDA(cudaSetDevice(devs[0]));
   AMX_CUDA(cudaEventCreate(&e0));
   AMX_CUDA(cudaEventCreate(&e1));
-  AMX_CUDA(cudaEventRecord(e0, stream()));
-  AMX_CUDA(cudaLaunchCooperativeKernel((void *)em_fit_kernel<DMAX>, dim3(grid), dim3(kEmThreads), args, smem, stream()));
-  count_launch();
-  AMX_CUDA(cudaEventRecord(e1, stream()));
-  AMX_CUDA(cudaEventSynchronize(e1));
-  AMX_CUDA(cudaEventElapsedTime(ms, e0, e1));
+  AMX_CUDA(cudaEventRecord(e0, st[0]));
+  int launched = 0;
+  for (int g = 0; g < ndev && rc == AMX_OK; g++) {
+    cudaSetDevice(devs[g]);
+    rc = em_launch_d(d, A[g], (unsigned)A[g].dev[g].grid, smem, st[g]);
+    if (rc == AMX_OK) launched++;
+  }
+  if (rc != AMX_OK && launched > 0) {
+    // a partner failed to start: tell the running kernels to stop (they poll their flags / public state)
+    EmPublic stop_pub;
+    memset(&stop_pub, 0, sizeof(stop_pub));
+    stop_pub.pass = kPassStop;
+    cudaStream_t side;
+    for (int g = 0; g < launched; g++) {
+      cudaSetDevice(devs[g]);
+      cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+      cudaMemcpyAsync(A[g].dev[g].pub, &stop_pub, sizeof(stop_pub), cudaMemcpyHostToDevice, side);
+      cudaMemsetAsync(A[g].dev[g].flags, 0xFF, sizeof(unsigned) * 8 * (size_t)A[g].dev[g].grid, side);
+      cudaStreamSynchronize(side);
+      cudaStreamDestroy(side);
+    }
+  }
+  cudaSetDevice(devs[0]);
+  cudaEventRecord(e1, st[0]);
+  for (int g = 0; g < launched; g++) {
+    cudaSetDevice(devs[g]);
+    cudaError_t e = cudaStreamSynchronize(st[g]);
+    if (e != cudaSuccess && rc == AMX_OK) rc = fail(AMX_ECUDA, "EM kernel on GPU %d: %s", devs[g], cudaGetErrorString(e));
+  }
+  cudaSetDevice(devs[0]);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+
+  int status = 0;
+  if (rc == AMX_OK) {
+    std::vector<char> hc(sizeof(EmCtrl));
+    AMX_CUDA(cudaMemcpy(hc.data(), ctrl, sizeof(EmCtrl), cudaMemcpyDeviceToHost));
+    const EmCtrl *c = reinterpret_cast<const EmCtrl *>(hc.data());
+    for (int l = 0; l < c->best_L; l++) {
+      wt[l] = c->best_lam[l];
+      for (int j = 0; j < d; j++) mean[(size_t)l * d + j] = c->best_mu[l][j];
+      for (int j = 0; j < tlen; j++) tri[(size_t)l * tlen + j] = c->best_B[l][j];
+    }
+    const int it = c->iters;
+    if (trace_L) AMX_CUDA(cudaMemcpy(trace_L, tr_L, sizeof(int) * it, cudaMemcpyDeviceToHost));
+    if (trace_ann) AMX_CUDA(cudaMemcpy(trace_ann, tr_ann, sizeof(int) * it, cudaMemcpyDeviceToHost));
+    if (trace_loglik) AMX_CUDA(cudaMemcpy(trace_loglik, tr_ll, sizeof(double) * it, cudaMemcpyDeviceToHost));
+    if (trace_cost) AMX_CUDA(cudaMemcpy(trace_cost, tr_cost, sizeof(double) * it, cudaMemcpyDeviceToHost));
+    if (cur_L) *cur_L = c->L;
+    for (int l = 0; l < c->L; l++) {
+      if (cur_wt) cur_wt[l] = c->lam[l];
+      if (cur_mean)
+        for (int j = 0; j < d; j++) cur_mean[(size_t)l * d + j] = c->mu[l][j];
+      if (cur_tri)
+        for (int j = 0; j < tlen; j++) cur_tri[(size_t)l * tlen + j] = c->B[l][j];
+    }
+    if (cur_w)
+      for (int g = 0; g < ndev; g++) {
+        cudaSetDevice(devs[g]);
+        AMX_CUDA(cudaMemcpy(cur_w + (size_t)off[g] * Lmax, A[g].w_out, sizeof(double) * (size_t)A[g].n * Lmax, cudaMemcpyDeviceToHost));
+      }
+    if (res) {
+      res->L = c->best_L;
+      res->iters = it;
+      res->status = c->status;
+      res->comp_steps = c->comp_steps;
+      res->kernel_ms = ms;
+      res->flops = c->flops;
+      res->bytes = 8.0 * d * (double)n * (double)c->comp_steps;
+    }
+    if (getenv("AMX_EM_DEBUG"))
+      fprintf(stderr, "[em dbg] %d GPU(s), cycles on GPU 0: block0 data pass %lld | leader: arrive-skew+reduce %lld logic %lld | block0 wait %lld reload %lld (phases ~%ld) | scatter passes %lld refresh passes %lld\n",
+              ndev, c->dbg[0], c->dbg[1], c->dbg[3], c->dbg[4], c->dbg[5], 2 * c->comp_steps, c->dbg[6], c->dbg[7]);
+    status = c->status;
+  }
+  for (int g = 0; g < ndev; g++) {
+    cudaSetDevice(devs[g]);
+    EmArgs &a = A[g];
+    if (x_host) cudaFree(const_cast<double *>(a.x));
+    cudaFree(a.xT); cudaFree(a.E); cudaFree(a.wnxt); cudaFree(a.w_out);
+    cudaFree(a.dev[g].part); cudaFree(a.dev[g].devrow); cudaFree(a.dev[g].flags); cudaFree(a.dev[g].arrive); cudaFree(a.dev[g].pub);
+    if (!(g == 0 && ndev == 1)) cudaStreamDestroy(st[g]);
+  }
+  cudaSetDevice(devs[0]);
+  cudaFree(ctrl); cudaFree(init_rows); cudaFree(tr_L); cudaFree(tr_ann); cudaFree(tr_ll); cudaFree(tr_cost);
+  cudaSetDevice(home);
+  if (rc != AMX_OK) return rc;
+  if (status == AMX_ECUDA) return fail(status, "EM fit: a GPU stopped answering at the cross-GPU barrier");
+  if (status) return fail(status, "EM fit: scatter matrix not positive definite");
   return AMX_OK;
 }
 
@@ -1107,93 +1433,8 @@ static int em_fit_impl(int d, long n, const double *x_dev, int Lmax, int maxit, 
                        double *mean, double *tri, int *trace_L, double *trace_loglik, double *trace_cost,
                        int *trace_ann, double *cur_wt, double *cur_mean, double *cur_tri, int *cur_L, double *cur_w,
                        amx_em_result *res) {
-  if (d < 1 || d > kEmDmax || Lmax < 1 || Lmax > kEmLmax || n < 1 || maxit < 0 || !init_idx || !wt || !mean || !tri)
-    return fail(AMX_EINVAL, "amx_em_fit: need 1<=d<=%d, 1<=Lmax<=%d, n>=1, maxit>=0 (got d=%d Lmax=%d n=%ld maxit=%d)",
-                kEmDmax, kEmLmax, d, Lmax, n, maxit);
-  if (n < Lmax) return fail(AMX_EINVAL, "amx_em_fit: fewer samples (%ld) than start components (%d)", n, Lmax);
-  for (int l = 0; l < Lmax; l++) {
-    if (init_idx[l] < 0 || init_idx[l] >= n) return fail(AMX_EINVAL, "amx_em_fit: init_idx[%d]=%d out of range", l, init_idx[l]);
-    for (int m = 0; m < l; m++)
-      if (init_idx[m] == init_idx[l]) return fail(AMX_EINVAL, "amx_em_fit: start rows must be distinct");
-  }
-  int dev = 0, sms = 0, coop = 0;
-  AMX_CUDA(cudaGetDevice(&dev));
-  AMX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  AMX_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-  if (!coop) return fail(AMX_ECUDA, "device lacks cooperative launch");
-  const int tlen = d * (d + 1) / 2, cap = maxit + 1;
-  EmArgs a;
-  memset(&a, 0, sizeof(a));
-  a.d = d;
-  a.Lmax = Lmax;
-  a.maxit = maxit;
-  a.n = n;
-  a.npad = (n + kEmThreads - 1) / kEmThreads * kEmThreads;  // whole tiles; the padding is zero and carries no weight
-  a.x = x_dev;
-  int *idx_dev = nullptr;
-  AMX_CUDA(cudaMalloc(&a.xT, sizeof(double) * (size_t)d * a.npad));
-  AMX_CUDA(cudaMalloc(&a.E, sizeof(double) * (size_t)Lmax * a.npad));
-  AMX_CUDA(cudaMalloc(&a.wnxt, sizeof(double) * (size_t)a.npad));
-  AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, stream()));
-  AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, stream()));
-  AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, stream()));
-  AMX_CUDA(cudaMalloc(&a.ctrl, sizeof(EmCtrl)));
-  AMX_CUDA(cudaMemsetAsync(a.ctrl, 0, sizeof(EmCtrl), stream()));
-  AMX_CUDA(cudaMalloc(&idx_dev, sizeof(int) * Lmax));
-  AMX_CUDA(cudaMemcpyAsync(idx_dev, init_idx, sizeof(int) * Lmax, cudaMemcpyHostToDevice, stream()));
-  a.init_idx = idx_dev;
-  AMX_CUDA(cudaMalloc(&a.trace_L, sizeof(int) * cap));
-  AMX_CUDA(cudaMalloc(&a.trace_ann, sizeof(int) * cap));
-  AMX_CUDA(cudaMalloc(&a.trace_loglik, sizeof(double) * cap));
-  AMX_CUDA(cudaMalloc(&a.trace_cost, sizeof(double) * cap));
-  if (cur_w) AMX_CUDA(cudaMalloc(&a.w_out, sizeof(double) * (size_t)n * Lmax));
-  float ms = 0;
-  int rc;
-  if (d <= 4) rc = em_launch<4>(a, sms, &ms);
-  else if (d <= 8) rc = em_launch<8>(a, sms, &ms);
-  else if (d <= 12) rc = em_launch<12>(a, sms, &ms);
-  else if (d <= 20) rc = em_launch<20>(a, sms, &ms);
-  else rc = em_launch<32>(a, sms, &ms);
-  if (rc) return rc;
-  std::vector<char> hc(sizeof(EmCtrl));
-  AMX_CUDA(cudaMemcpy(hc.data(), a.ctrl, sizeof(EmCtrl), cudaMemcpyDeviceToHost));
-  const EmCtrl *c = reinterpret_cast<const EmCtrl *>(hc.data());
-  for (int l = 0; l < c->best_L; l++) {
-    wt[l] = c->best_lam[l];
-    for (int j = 0; j < d; j++) mean[(size_t)l * d + j] = c->best_mu[l][j];
-    for (int j = 0; j < tlen; j++) tri[(size_t)l * tlen + j] = c->best_B[l][j];
-  }
-  const int it = c->iters;
-  if (trace_L) AMX_CUDA(cudaMemcpy(trace_L, a.trace_L, sizeof(int) * it, cudaMemcpyDeviceToHost));
-  if (trace_ann) AMX_CUDA(cudaMemcpy(trace_ann, a.trace_ann, sizeof(int) * it, cudaMemcpyDeviceToHost));
-  if (trace_loglik) AMX_CUDA(cudaMemcpy(trace_loglik, a.trace_loglik, sizeof(double) * it, cudaMemcpyDeviceToHost));
-  if (trace_cost) AMX_CUDA(cudaMemcpy(trace_cost, a.trace_cost, sizeof(double) * it, cudaMemcpyDeviceToHost));
-  if (cur_L) *cur_L = c->L;
-  for (int l = 0; l < c->L; l++) {
-    if (cur_wt) cur_wt[l] = c->lam[l];
-    if (cur_mean)
-      for (int j = 0; j < d; j++) cur_mean[(size_t)l * d + j] = c->mu[l][j];
-    if (cur_tri)
-      for (int j = 0; j < tlen; j++) cur_tri[(size_t)l * tlen + j] = c->B[l][j];
-  }
-  if (cur_w) AMX_CUDA(cudaMemcpy(cur_w, a.w_out, sizeof(double) * (size_t)n * Lmax, cudaMemcpyDeviceToHost));
-  if (res) {
-    res->L = c->best_L;
-    res->iters = it;
-    res->status = c->status;
-    res->comp_steps = c->comp_steps;
-    res->kernel_ms = ms;
-    res->flops = c->flops;
-    res->bytes = 8.0 * d * (double)n * (double)c->comp_steps;
-  }
-  if (getenv("AMX_EM_DEBUG"))
-    fprintf(stderr, "[em dbg] cycles: block0 data pass %lld | leader: arrive-skew %lld reduce %lld logic %lld | block0 wait %lld reload %lld (phases ~%ld) | scatter passes %lld refresh passes %lld\n",
-            c->dbg[0], c->dbg[1], c->dbg[2], c->dbg[3], c->dbg[4], c->dbg[5], 2 * c->comp_steps, c->dbg[6], c->dbg[7]);
-  const int status = c->status;
-  cudaFree(a.xT); cudaFree(a.E); cudaFree(a.wnxt); cudaFree(a.ctrl); cudaFree(idx_dev); cudaFree(a.part); cudaFree(a.flags);
-  cudaFree(a.trace_L); cudaFree(a.trace_ann); cudaFree(a.trace_loglik); cudaFree(a.trace_cost); cudaFree(a.w_out);
-  if (status) return fail(status, "EM fit: scatter matrix not positive definite");
-  return AMX_OK;
+  return em_fit_general(1, nullptr, d, n, nullptr, x_dev, Lmax, maxit, init_idx, wt, mean, tri, trace_L, trace_loglik,
+                        trace_cost, trace_ann, cur_wt, cur_mean, cur_tri, cur_L, cur_w, res);
 }
 
 extern "C" {
@@ -1232,6 +1473,16 @@ int amx_em_fit(int d, long n, const double *x, int Lmax, int maxit, const int *i
                        cur_wt, cur_mean, cur_tri, cur_L, cur_w, res);
   cudaFree(x_dev);
   return rc;
+}
+
+int amx_em_fit_multi(int ndev, const int *devices, int d, long n, const double *x, int Lmax, int maxit,
+                     const int *init_idx, double *wt, double *mean, double *tri, int *trace_L, double *trace_loglik,
+                     double *trace_cost, int *trace_ann, double *cur_wt, double *cur_mean, double *cur_tri, int *cur_L,
+                     double *cur_w, amx_em_result *res) {
+  if (int rc = require_device()) return rc;
+  if (!x || !devices) return fail(AMX_EINVAL, "amx_em_fit_multi: null samples or device list");
+  return em_fit_general(ndev, devices, d, n, x, nullptr, Lmax, maxit, init_idx, wt, mean, tri, trace_L, trace_loglik,
+                        trace_cost, trace_ann, cur_wt, cur_mean, cur_tri, cur_L, cur_w, res);
 }
 
 int amx_autorj_fit(int d, long n, const double *x, double *wt, double *mean, double *tri) {

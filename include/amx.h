@@ -204,6 +204,15 @@ int amx_em_fit_dev(int d, long n, const double *x_dev, int Lmax, int maxit,
                    const int *init_idx, double *wt, double *mean, double *tri,
                    int *trace_L, double *trace_loglik, double *trace_cost,
                    int *trace_ann, amx_em_result *res);
+/* The same fit with the samples sharded over ndev GPUs of one box (contiguous blocks of rows).  Every GPU
+ * runs the same persistent kernel on its shard; per pass they exchange only the partial sufficient statistics
+ * (column sums, log-likelihood, first moment or centred scatter: <= 2 KB per GPU) through NVLink peer memory
+ * inside the kernel, reduced in fixed GPU order, so every GPU takes the same annihilation / convergence
+ * branches.  devices: CUDA ordinals.  One host thread drives all GPUs. */
+int amx_em_fit_multi(int ndev, const int *devices, int d, long n, const double *x, int Lmax, int maxit,
+                     const int *init_idx, double *wt, double *mean, double *tri, int *trace_L,
+                     double *trace_loglik, double *trace_cost, int *trace_ann, double *cur_wt,
+                     double *cur_mean, double *cur_tri, int *cur_L, double *cur_w, amx_em_result *res);
 /* Distinct start rows from a uniform stream exactly as :682-697; returns the
  * number of uniforms consumed. */
 long amx_em_draw_init(long n, int Lmax, const double *uniforms, long nuniforms,
