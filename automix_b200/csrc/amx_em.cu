@@ -140,19 +140,35 @@ __device__ __forceinline__ int barrier_arrive(const EmArgs &a, unsigned &epoch, 
   if (!s_last) return 0;
   if (nv > 0) leader_reduce(me.part, nv, s_tot, s_chunk);  // this GPU's CTAs, coalesced, fixed order
   if (a.ndev == 1) return 2;
-  for (int q = threadIdx.x; q < nv; q += blockDim.x) __stcg(me.devrow + q, s_tot[q]);
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd_system(&a.ctrl->arrive, 1u);
-    s_last = (t == (unsigned)a.ndev * (epoch + 1u) - 1u) ? 1 : 0;
+  // The leader is always GPU 0's last CTA: the control block lives in GPU 0's memory, so the sequential
+  // section runs on local memory; the other GPUs post their reduced row and a remote arrival and go to wait.
+  if (a.rank != 0) {
+    for (int q = threadIdx.x; q < nv; q += blockDim.x) __stcg(me.devrow + q, s_tot[q]);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd_system(&a.ctrl->arrive, 1u);
+    return 1;
+  }
+  if (threadIdx.x == 0) {  // wait (on local memory) until every other GPU has arrived
+    const unsigned want = (unsigned)(a.ndev - 1) * (epoch + 1u);
+    const long long t0 = clock64();
+    unsigned ns = 32;
+    s_last = 1;
+    while (ld_cg(&a.ctrl->arrive) < want) {
+      __nanosleep(ns);
+      if (ns < 256) ns *= 2;
+      if (clock64() - t0 > 40000000000LL) {
+        s_last = 0;  // a GPU never arrived: let the watchdog of the waiters end the kernel
+        break;
+      }
+    }
     __threadfence_system();
   }
   __syncthreads();
   if (!s_last) return 1;
-  for (int q = threadIdx.x; q < nv; q += blockDim.x) {  // the per-GPU rows, in GPU order
-    double t = 0.0;
-    for (int g = 0; g < a.ndev; g++) t += ld_cg(a.dev[g].devrow + q);
+  for (int q = threadIdx.x; q < nv; q += blockDim.x) {  // GPU 0's own sum first, then the others' rows in GPU order
+    double t = s_tot[q];
+    for (int g = 1; g < a.ndev; g++) t += ld_cg(a.dev[g].devrow + q);
     s_tot[q] = t;
   }
   __syncthreads();

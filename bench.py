@@ -304,6 +304,20 @@ def main():
         for _ in range(e2e_fits):
             r2 = amx.em_fit(x_pin.numpy(), idx, Lmax=L, maxit=args.em_maxit)  # H2D of x inside
         t_e2e = (time.perf_counter() - t0) / e2e_fits
+        em_multi = None
+        if world > 1:
+            # the same fit with the samples sharded over all N GPUs of the box (strong scaling: n fixed); rank 0
+            # drives every GPU, the shards exchange their partial sums through NVLink inside the kernel
+            devs = list(range(world))
+            rm = amx.em_fit(x, idx, Lmax=L, maxit=args.em_maxit, devices=devs)
+            tms = []
+            for _ in range(args.em_steps):
+                rm = amx.em_fit(x, idx, Lmax=L, maxit=args.em_maxit, devices=devs)
+                tms.append(rm["kernel_ms"])
+            tm_fit = float(np.mean(tms)) * 1e-3
+            em_multi = {"n_gpus": world, "scaling": "strong", "value": n * rm["iters"] / tm_fit, "ms_per_fit": 1e3 * tm_fit,
+                        "same_trace_as_single_gpu": bool(np.array_equal(rm["trace_L"], r["trace_L"])),
+                        "exchange": "per pass <= 2 KB per GPU through NVLink peer memory inside the kernel, fixed GPU order"}
         em = {"metric": "EM-fit samples/s", "value": n * its / t_fit, "unit": "EM-fit samples/s",
               "ms_per_fit": 1e3 * t_fit, "outer_iterations": its, "component_steps": int(steps_),
               "sample_component_steps_per_s": n * steps_ / t_fit, "final_L": int(r["L"]),
@@ -325,6 +339,8 @@ def main():
               "e2e": {"value": n * r2["iters"] / t_e2e, "unit": "EM-fit samples/s",
                       "h2d_bytes_per_step": int(x.nbytes + 4 * L), "d2h_bytes_per_step": int(8 * L * (1 + d + d * (d + 1) // 2) + 24 * its)},
               "gpu_launches": int(em_launches)}
+        if em_multi is not None:
+            em["sharded"] = em_multi
         del x_dev
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1 only)
