@@ -131,10 +131,14 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   if (threadIdx.x < nm) s_clp[threadIdx.x] = T.flops(threadIdx.x);
   __syncthreads();
 
-  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int status = 0;
+  // The grid may be smaller than the population (large configurations keep few threads resident so that a
+  // chain's scratch vectors stay in L1): every thread then walks several chains, one after the other.
+  for (long base = (long)blockIdx.x * blockDim.x; base < a.st.C; base += (long)gridDim.x * blockDim.x) {
+  const long gid = base + threadIdx.x;
   const bool active = gid < a.st.C;
   const long id = active ? gid : a.st.C - 1;  // tail lanes shadow the last chain, never write
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   ChainRegs<CFG> c;
   load_chain(c, a.st, id);
@@ -142,7 +146,6 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   const unsigned long long draws0 = a.st.draws[id];
   open_stream(u, a, id, draws0);
   const bool traced = active && gid < a.ntrace;
-  int status = 0;
 
   for (int s = 0; s < a.nsweeps; s++) {
     const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
     const unsigned long long r = warp_sum_u64(active ? v[q] : 0ull);
     if (lane == 0) atomicAdd(&s_cnt[q], r);
   }
+  }  // chains of this thread
   if (status) atomicOr(&s_status, status);
   __syncthreads();
   if (threadIdx.x < 8) atomicAdd(&a.cnt[threadIdx.x], s_cnt[threadIdx.x]);
@@ -458,11 +462,25 @@ struct amx_rj {
 template <class CFG, class TGT, class RNG>
 static int launch_sweeps(const RjLaunch &a) {
   const size_t need = (size_t)a.prop_bytes + (size_t)a.tgt_bytes;
-  int staged = need <= 200 * 1024 ? 1 : 0;
+  int staged = need <= 160 * 1024 ? 1 : 0;
   const size_t smem = staged ? need : 0;
   auto kern = rj_sweep_kernel<CFG, TGT, RNG>;
   if (smem > 48 * 1024) AMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((a.st.C + kRjThreads - 1) / kRjThreads);
+  unsigned grid = (unsigned)((a.st.C + kRjThreads - 1) / kRjThreads);
+  if (CFG::DMAX > 8) {
+    // Large configurations keep a chain's vectors (~1-1.8 KB per thread) in local memory.  At full
+    // occupancy that is > 1 MB per SM and spills past L1 and L2; with a couple of resident CTAs per SM it stays
+    // in L1, so cap the grid and let the kernel's chain loop cover the population.
+    int dev = 0, sms = 0;
+    AMX_CUDA(cudaGetDevice(&dev));
+    AMX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const char *e = getenv("AMX_RJ_BLOCKS_PER_SM");
+    const unsigned per_sm = e ? (unsigned)atoi(e) : (CFG::DMAX <= 20 ? 2u : 1u);
+    const unsigned cap = (unsigned)sms * (per_sm ? per_sm : 1u);
+    if (grid > cap) grid = cap;
+    AMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  staged ? (int)((smem * per_sm * 100) / (228 * 1024) + 5) : 0));
+  }
   kern<<<grid, kRjThreads, smem, stream()>>>(a, staged);
   count_launch();
   AMX_CUDA(cudaGetLastError());
@@ -472,10 +490,12 @@ static int launch_sweeps(const RjLaunch &a) {
 template <class TGT, class RNG>
 static int launch_cfg(const RjLaunch &a, int dmax, int Lmax, int nm) {
   if constexpr (std::is_same<TGT, CoalTarget>::value) {
+    if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
     return launch_sweeps<RjCfgG, TGT, RNG>(a);
   } else {
     if (dmax <= RjCfgS::DMAX && Lmax <= RjCfgS::LMAX && nm <= RjCfgS::NMAX) return launch_sweeps<RjCfgS, TGT, RNG>(a);
     if (dmax <= RjCfgM::DMAX && Lmax <= RjCfgM::LMAX && nm <= RjCfgM::NMAX) return launch_sweeps<RjCfgM, TGT, RNG>(a);
+    if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
     return launch_sweeps<RjCfgG, TGT, RNG>(a);
   }
 }

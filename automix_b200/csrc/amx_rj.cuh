@@ -18,6 +18,7 @@ struct RjCfg {
 };
 using RjCfgS = RjCfg<2, 8, 2>;     // toy1-sized: everything in registers
 using RjCfgM = RjCfg<8, 8, 8>;     // toy2 / tutorial-sized
+using RjCfgL = RjCfg<20, 8, 16>;   // large: coal-mining (d<=13), the scaling workload (d<=20); ~1 KB of local vectors
 using RjCfgG = RjCfg<AMX_MAX_DIM, AMX_MAX_COMPS, AMX_MAX_MODELS>;  // general (local memory)
 
 constexpr double kHalfLog2Pi = 0.9189385332046727;  // literal at automix.c:1052
