@@ -44,7 +44,7 @@ EXPORTS = [
     "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
-    "amx_rj_set_tape", "amx_rj_set_chain_base", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
+    "amx_rj_set_tape", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
     "amx_rj_collect", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_em_fit", "amx_em_fit_dev",
     "amx_em_draw_init", "amx_em_fit_multi", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
 ]
@@ -84,6 +84,8 @@ def lib():
     L.amx_rj_destroy.argtypes = [C.c_void_p]
     L.amx_rj_set_tape.argtypes = [C.c_void_p, _dp, C.c_long]
     L.amx_rj_set_chain_base.argtypes = [C.c_void_p, C.c_uint64]
+    L.amx_rj_set_modes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.amx_rwm_set_dof.argtypes = [C.c_int]
     L.amx_copy_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.amx_rj_init_chains.argtypes = [C.c_void_p]
     L.amx_rj_set_state.argtypes = [C.c_void_p, C.c_long, C.c_long, _dp, _dp, _dp, _ip, _ip, _dp, C.c_ulonglong]
@@ -248,6 +250,9 @@ class RjPopulation:
             raise AmxError(L.amx_last_error().decode())
         self.last_nsweeps = 0
 
+    def set_modes(self, dof=0, do_perm=False):
+        check(lib().amx_rj_set_modes(self.h, int(dof), int(do_perm)))
+
     def set_chain_base(self, first_chain_id: int):
         check(lib().amx_rj_set_chain_base(self.h, int(first_chain_id)))
 
@@ -397,8 +402,9 @@ def autorj_fit(x):
     return dict(lam=wt, mu=mean, B=tri)
 
 
-def rwm_adapt(target: Target, model_k: int, nsweep2: int, nchains: int, init, seed=0, tapes=None):
+def rwm_adapt(target: Target, model_k: int, nsweep2: int, nchains: int, init, seed=0, tapes=None, dof=0):
     """Stage-1 adaptive RWM for one model on the GPU (amx_rwm_adapt)."""
+    check(lib().amx_rwm_set_dof(int(dof)))
     d = int(target.dims[model_k])
     init = f64(init)
     nsw = max(nsweep2, 10000 * d)

@@ -181,4 +181,55 @@ __device__ __forceinline__ void gauss_pair(U &u, double &z0, double &z1) {
   z1 = r * c;
 }
 
+// ---- Student-t proposals and random permutation (optional modes of the sampler) -----------------------
+// Gamma(s,1) by rejection, three regimes, exactly the draw order of rgamma() (automix.c:1585-1637).
+template <class U>
+__device__ __forceinline__ double rgamma_dev(double s, U &u) {
+  const double e1 = 2.718281828459045;  // exp(1.0)
+  double out;
+  if (s < 1.0) {
+    const double b = (s + e1) / e1, inv = 1.0 / s;
+    for (;;) {
+      const double bu = b * u.next();
+      if (bu <= 1.0) {
+        const double t = inv * log(bu);
+        out = exp(t < -30.0 ? -30.0 : t);
+        if (u.next() < exp(-out)) break;
+      } else {
+        out = -log((b - bu) / s);
+        if (u.next() < pow(out, s - 1.0)) break;
+      }
+      if (u.overrun()) break;
+    }
+  } else if (s == 1.0) {
+    out = -log(u.next());
+  } else {
+    const double c1 = s - 1.0, c2 = (s - 1.0 / (6.0 * s)) / c1, c3 = 2.0 / c1, c4 = c3 + 2.0, c5 = 1.0 / sqrt(s);
+    double w = 1.0;
+    for (;;) {
+      double u1 = u.next();
+      const double u2 = u.next();
+      if (s > 2.5) u1 = u2 + c5 * (1.0 - 1.86 * u1);
+      if (u.overrun()) break;
+      if (u1 <= 0.0 || u1 >= 1.0) continue;
+      w = c2 * u2 / u1;
+      if ((c3 * u1 + w + 1.0 / w) <= c4) break;
+      if ((c3 * log(u1) - log(w) + w) >= 1.0) continue;
+      break;
+    }
+    out = c1 * w;
+  }
+  return out;
+}
+// the common divisor of one rt() call: sqrt(Gamma(dof/2) / (dof/2)) (automix.c:1672-1677)
+template <class U>
+__device__ __forceinline__ double t_divisor(int dof, U &u) {
+  const double s = 0.5 * dof;
+  return sqrt(rgamma_dev(s, u) / s);
+}
+// log density of a t variate (automix.c:1717-1725); lt_const = lgamma((dof+1)/2) - lgamma(dof/2) - log(dof*pi)/2
+__device__ __forceinline__ double ltprob_dev(int dof, double lt_const, double z) {
+  return lt_const - 0.5 * (dof + 1) * log(1.0 + (z * z) / dof);
+}
+
 }  // namespace amx

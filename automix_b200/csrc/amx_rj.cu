@@ -7,6 +7,7 @@
 // is no per-sweep global traffic except the optional trace chains.  Model-visit counts are
 // accumulated with warp-aggregated ballots into a per-warp shared histogram and flushed with
 // one 64-bit atomic per model per CTA.
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -133,6 +134,9 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int status = 0;
+  // optional modes are compiled out of the small configuration (a run that asks for them takes the medium one)
+  typename std::conditional<(CFG::DMAX <= 2), NoModes, RjModes>::type md;
+  if constexpr (CFG::DMAX > 2) md = a.modes;
   // The grid may be smaller than the population (large configurations keep few threads resident so that a
   // chain's scratch vectors stay in L1): every thread then walks several chains, one after the other.
   for (long base = (long)blockIdx.x * blockDim.x; base < a.st.C; base += (long)gridDim.x * blockDim.x) {
@@ -151,20 +155,20 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
     const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
     const int d = P.h->dims[c.k];
     if (sweep_i % 10ull == 0ull) {  // block move every 10th sweep (:95, :148)
-      rwm_block_propose(c, P, u);
+      rwm_block_propose(c, P, u, md);
       const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
       rwm_block_finish(c, P, u, lpn);
       c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
     } else {
       sync_proposal(c, d);
       for (int j = 0; j < d; j++) {
-        rwm_coord_propose(c, P, u, j);
+        rwm_coord_propose(c, P, u, j, md);
         const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
         rwm_coord_finish(c, u, j, lpn);
       }
       c.flops += (unsigned)(d * (s_clp[c.k] + 12));
     }
-    rj_propose(c, P, u, a.gam[s], 0, s_clp);
+    rj_propose(c, P, u, a.gam[s], md, s_clp);
     const double lpn = eval_target<CFG, TGT>(T, c.kn, c.thn);
     rj_finish(c, P, u, lpn, a.adapt != 0);
     if (c.lp != c.lp) status |= 2;
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
   int keval = -1;
   switch (phase) {
     case kPhBlockPropose:
-      rwm_block_propose(c, P, u);
+      rwm_block_propose(c, P, u, a.modes);
       keval = c.k;
       break;
     case kPhBlockFinish:
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
     case kPhCoordPropose:
       if (j == 0) sync_proposal(c, d);
       if (j < d) {
-        rwm_coord_propose(c, P, u, j);
+        rwm_coord_propose(c, P, u, j, a.modes);
         keval = c.k;
       }
       break;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
       if (j < d) rwm_coord_finish(c, u, j, lpn);
       break;
     case kPhJumpPropose:
-      rj_propose(c, P, u, a.gam[s], 0, s_clp);
+      rj_propose(c, P, u, a.gam[s], a.modes, s_clp);
       keval = c.kn;
       break;
     case kPhJumpFinish:
@@ -435,6 +439,7 @@ struct amx_rj {
   long C;
   int dmax, nm, ntrace;
   unsigned long long seed, sweep_i, chain_base;
+  RjModes modes;
   RjState st;
   double *init_dev;
   double *tape_dev;
@@ -493,7 +498,8 @@ static int launch_cfg(const RjLaunch &a, int dmax, int Lmax, int nm) {
     if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
     return launch_sweeps<RjCfgG, TGT, RNG>(a);
   } else {
-    if (dmax <= RjCfgS::DMAX && Lmax <= RjCfgS::LMAX && nm <= RjCfgS::NMAX) return launch_sweeps<RjCfgS, TGT, RNG>(a);
+    const bool plain = a.modes.dof == 0 && a.modes.do_perm == 0;
+    if (plain && dmax <= RjCfgS::DMAX && Lmax <= RjCfgS::LMAX && nm <= RjCfgS::NMAX) return launch_sweeps<RjCfgS, TGT, RNG>(a);
     if (dmax <= RjCfgM::DMAX && Lmax <= RjCfgM::LMAX && nm <= RjCfgM::NMAX) return launch_sweeps<RjCfgM, TGT, RNG>(a);
     if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
     return launch_sweeps<RjCfgG, TGT, RNG>(a);
@@ -522,6 +528,7 @@ static RjLaunch base_launch(const amx_rj *rj) {
   a.tgt_flags = rj->tgt->d.flags;
   a.seed = rj->seed;
   a.chain_base = rj->chain_base;
+  a.modes = rj->modes;
   a.tape = rj->tape_dev;
   a.tape_stride = rj->tape_stride;
   a.visits = rj->visits_dev;
@@ -698,6 +705,16 @@ void amx_rj_destroy(amx_rj *rj) {
   delete rj->h_xc;
   delete rj->h_lc;
   delete rj;
+}
+
+int amx_rj_set_modes(amx_rj *rj, int student_t_dof, int do_perm) {
+  if (!rj || student_t_dof < 0) return fail(AMX_EINVAL, "amx_rj_set_modes: bad arguments");
+  rj->modes.dof = student_t_dof;
+  rj->modes.do_perm = do_perm ? 1 : 0;
+  rj->modes.lt_const = student_t_dof > 0 ? lgamma(0.5 * (student_t_dof + 1)) - lgamma(0.5 * student_t_dof) -
+                                               0.5 * log(student_t_dof * 3.14159265358979323846)
+                                         : 0.0;
+  return AMX_OK;
 }
 
 int amx_rj_set_chain_base(amx_rj *rj, uint64_t first_chain_id) {

@@ -23,6 +23,18 @@ using RjCfgG = RjCfg<AMX_MAX_DIM, AMX_MAX_COMPS, AMX_MAX_MODELS>;  // general (l
 
 constexpr double kHalfLog2Pi = 0.9189385332046727;  // literal at automix.c:1052
 
+// optional modes (amSampler.student_T_dof, amSampler.doPerm)
+// compile-time "no optional modes": the branches below fold away (the small configuration uses this)
+struct NoModes {
+  static constexpr int dof = 0, do_perm = 0;
+  static constexpr double lt_const = 0.0;
+};
+struct RjModes {
+  int dof;          // 0: Gaussian innovations
+  int do_perm;      // random permutation of the standardised vector (automix.c:1184-1194)
+  double lt_const;  // constant of ltprob for this dof
+};
+
 // Read-only view of the proposal family blob (include/amx_layout.h).
 struct ProposalView {
   const amx_fam_hdr *h;
@@ -53,19 +65,31 @@ struct ChainRegs {
 };
 
 // ---- within-model RWM (:1056-1085) -------------------------------------------------------
-template <class CFG, class U>
-__device__ __forceinline__ void rwm_block_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u) {
+template <class CFG, class U, class MD>
+__device__ __forceinline__ void rwm_block_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, const MD &md) {
   const int d = P.h->dims[c.k];
   const double *sg = P.sig(c.k);
   c.try_b++;
   int i = 0;
-  for (; i + 1 < d; i += 2) {
-    double z0, z1;
-    gauss_pair(u, z0, z1);
-    aset(c.thn, i, fma(sg[i], z0, aget(c.th, i)));
-    aset(c.thn, i + 1, fma(sg[i + 1], z1, aget(c.th, i + 1)));
+  if (md.dof == 0) {
+    for (; i + 1 < d; i += 2) {
+      double z0, z1;
+      gauss_pair(u, z0, z1);
+      aset(c.thn, i, fma(sg[i], z0, aget(c.th, i)));
+      aset(c.thn, i + 1, fma(sg[i + 1], z1, aget(c.th, i + 1)));
+    }
+    if (d & 1) aset(c.thn, d - 1, fma(sg[d - 1], gauss_single(u), aget(c.th, d - 1)));
+  } else {  // rt(): all the normals first, then ONE gamma draw scales them (automix.c:1663-1680)
+    for (; i + 1 < d; i += 2) {
+      double z0, z1;
+      gauss_pair(u, z0, z1);
+      aset(c.thn, i, z0);
+      aset(c.thn, i + 1, z1);
+    }
+    if (d & 1) aset(c.thn, d - 1, gauss_single(u));
+    const double den = t_divisor(md.dof, u);
+    for (int j = 0; j < d; j++) aset(c.thn, j, fma(sg[j], aget(c.thn, j) / den, aget(c.th, j)));
   }
-  if (d & 1) aset(c.thn, d - 1, fma(sg[d - 1], gauss_single(u), aget(c.th, d - 1)));
 }
 template <class CFG, class U>
 __device__ __forceinline__ void rwm_block_finish(ChainRegs<CFG> &c, const ProposalView &P, U &u, double lpn) {
@@ -82,10 +106,12 @@ __device__ __forceinline__ void rwm_block_finish(ChainRegs<CFG> &c, const Propos
   }
 }
 // coordinate j (the caller guarantees j < d for active lanes)
-template <class CFG, class U>
-__device__ __forceinline__ void rwm_coord_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, int j) {
+template <class CFG, class U, class MD>
+__device__ __forceinline__ void rwm_coord_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, int j, const MD &md) {
   c.try_s++;
-  aset(c.thn, j, fma(P.sig(c.k)[j], gauss_single(u), aget(c.th, j)));
+  double z = gauss_single(u);
+  if (md.dof > 0) z /= t_divisor(md.dof, u);
+  aset(c.thn, j, fma(P.sig(c.k)[j], z, aget(c.th, j)));
 }
 template <class CFG, class U>
 __device__ __forceinline__ void rwm_coord_finish(ChainRegs<CFG> &c, U &u, int j, double lpn) {
@@ -119,9 +145,9 @@ __device__ __forceinline__ void alloc_probs(const ProposalView &P, int k, const 
 }
 
 // ---- between-model move, everything up to the log-posterior of the proposal -------------
-template <class CFG, class U>
+template <class CFG, class U, class MD>
 __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, double gam,
-                                           int clp_k, const int *clp_tab) {
+                                           const MD &md, const int *clp_tab) {
   const int nm = P.h->nmodels;
   const int k = c.k, d = P.h->dims[k], L = P.h->ncomp[k];
   double pa[CFG::LMAX];
@@ -183,7 +209,17 @@ __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView
       }
     }
   }
-  // 9.4 dimension matching (:1173-1204), Gaussian innovations (dof = 0, doPerm = 0)
+  // 9.4 dimension matching (:1173-1204)
+  auto permute = [&](int n) {  // perm() (:1703-1715): n-1 uniforms
+    for (int i = 0; i < n - 1; i++) {
+      const int j = i + (int)((n - i) * u.next());
+      if (j != i) {
+        const double t = aget(wk, j);
+        aset(wk, j, aget(wk, i));
+        aset(wk, i, t);
+      }
+    }
+  };
   if (d < dn) {
     int i = d;
     for (; i + 1 < dn; i += 2) {
@@ -193,14 +229,28 @@ __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView
       aset(wk, i + 1, z1);
     }
     if ((dn - d) & 1) aset(wk, dn - 1, gauss_single(u));
-    for (int j = d; j < dn; j++) {
-      const double w = aget(wk, j);
-      lr += 0.5 * (w * w) + kHalfLog2Pi;
+    if (md.dof > 0) {
+      const double den = t_divisor(md.dof, u);
+      for (int j = d; j < dn; j++) aset(wk, j, aget(wk, j) / den);
+      for (int j = d; j < dn; j++) lr -= ltprob_dev(md.dof, md.lt_const, aget(wk, j));
+    } else {
+      for (int j = d; j < dn; j++) {
+        const double w = aget(wk, j);
+        lr += 0.5 * (w * w) + kHalfLog2Pi;
+      }
     }
-  } else if (d > dn) {
-    for (int j = dn; j < d; j++) {
-      const double w = aget(wk, j);
-      lr -= (0.5 * (w * w) + kHalfLog2Pi);
+    if (md.do_perm) permute(dn);
+  } else if (d == dn) {
+    if (md.do_perm) permute(d);
+  } else {
+    if (md.do_perm) permute(d);
+    if (md.dof > 0) {
+      for (int j = dn; j < d; j++) lr += ltprob_dev(md.dof, md.lt_const, aget(wk, j));
+    } else {
+      for (int j = dn; j < d; j++) {
+        const double w = aget(wk, j);
+        lr -= (0.5 * (w * w) + kHalfLog2Pi);
+      }
     }
   }
   // map through component ln of model kn (:1206-1211)
@@ -239,7 +289,6 @@ __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView
   c.t_det = recn[2] - recl[2];
   const int dd = d > dn ? d - dn : dn - d;
   c.flops += (unsigned)(d * d + d + dn * dn + 2 * dn + clp_tab[kn] + 4 * dd + 4 * nm + Ln + 27);
-  (void)clp_k;
 }
 
 // 9.6 accept/reject and pk adaptation (:1238-1282).  Returns the model after the sweep.
@@ -338,6 +387,7 @@ struct RjLaunch {
   unsigned long long sweep0;   // sweep_i of the first sweep of this launch
   int nsweeps;
   int adapt;                   // doAdapt && !isBurning
+  RjModes modes;
   // outputs
   unsigned long long *visits;  // [nmodels]
   unsigned long long *cnt;     // [8]: 6 runStats counters, flops, draws

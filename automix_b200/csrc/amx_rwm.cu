@@ -23,6 +23,7 @@ struct RwmArgs {
   const void *tgt_blob;
   int tgt_flags;
   int model_k, d;
+  int dof;                // Student-t proposals when > 0 (rt(), automix.c:1663-1680)
   int nsweepr, nburn;     // total sweeps (incl. the extra tenth), and the adaptation-only prefix
   long nchains;
   const double *init;     // [d]
@@ -76,10 +77,15 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_adapt_kernel(RwmArgs a) {
       for (; i + 1 < d; i += 2) {
         double z0, z1;
         gauss_pair(u, z0, z1);
-        aset(prop, i, fma(aget(sig, i), z0, aget(cur, i)));
-        aset(prop, i + 1, fma(aget(sig, i + 1), z1, aget(cur, i + 1)));
+        aset(prop, i, z0);
+        aset(prop, i + 1, z1);
       }
-      if (d & 1) aset(prop, d - 1, fma(aget(sig, d - 1), gauss_single(u), aget(cur, d - 1)));
+      if (d & 1) aset(prop, d - 1, gauss_single(u));
+      const double den = a.dof > 0 ? t_divisor(a.dof, u) : 1.0;
+      for (int j = 0; j < d; j++) {
+        const double z = a.dof > 0 ? aget(prop, j) / den : aget(prop, j);
+        aset(prop, j, fma(aget(sig, j), z, aget(cur, j)));
+      }
       const double lpn = T.template eval<DMAX>(k, prop);
       if (u.next() < mh_prob(lpn - lp)) {
 #pragma unroll
@@ -92,7 +98,8 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_adapt_kernel(RwmArgs a) {
     } else {  // coordinate-wise moves with scale adaptation (:618-640)
       const double gam = a.gtab[sweep - 1];
       for (int i = 0; i < d; i++) {
-        const double z = gauss_single(u);
+        double z = gauss_single(u);
+        if (a.dof > 0) z /= t_divisor(a.dof, u);
         const double si = aget(sig, i);
         aset(prop, i, fma(si, z, aget(cur, i)));
         const double lpn = T.template eval<DMAX>(k, prop);
@@ -233,17 +240,23 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_split_kernel(RwmArgs a, RwmSp
       for (; i + 1 < d; i += 2) {
         double z0, z1;
         gauss_pair(u, z0, z1);
-        prop[i] = fma(sig[i], z0, cur[i]);
-        prop[i + 1] = fma(sig[i + 1], z1, cur[i + 1]);
+        prop[i] = z0;
+        prop[i + 1] = z1;
       }
-      if (d & 1) prop[d - 1] = fma(sig[d - 1], gauss_single(u), cur[d - 1]);
+      if (d & 1) prop[d - 1] = gauss_single(u);
+      const double den = a.dof > 0 ? t_divisor(a.dof, u) : 1.0;
+      for (int q = 0; q < d; q++) prop[q] = fma(sig[q], a.dof > 0 ? prop[q] / den : prop[q], cur[q]);
     } else {
-      prop[0] = fma(sig[0], gauss_single(u), cur[0]);
+      double z = gauss_single(u);
+      if (a.dof > 0) z /= t_divisor(a.dof, u);
+      prop[0] = fma(sig[0], z, cur[0]);
     }
     keval = k;
   } else if (j < d) {
     if (mode == 0) {
-      prop[j] = fma(sig[j], gauss_single(u), cur[j]);
+      double z = gauss_single(u);
+      if (a.dof > 0) z /= t_divisor(a.dof, u);
+      prop[j] = fma(sig[j], z, cur[j]);
       keval = k;
     }
   } else {  // j == d: end of sweep (:642-655)
@@ -377,6 +390,8 @@ using namespace amx;
 
 // One stage-1 run = allocate + enqueue (start) and wait + read back (finish); splitting the two lets
 // the runs of all models be in flight at once on separate streams (amx_rwm_adapt_all).
+static int g_rwm_dof = 0;  // process-wide, like the reference's sampler flags (amSampler.student_T_dof)
+
 struct RwmJob {
   RwmArgs a;
   double *init_dev, *gtab, *tape_dev, *sig_dev, *samp_dev, *tr_dev;
@@ -401,6 +416,7 @@ static int rwm_job_start(const amx_target *t, int model_k, int nsweep2, long nch
   a.d = d;
   a.nchains = nchains;
   a.seed = seed;
+  a.dof = g_rwm_dof;
   J.nstore = 1000L * d;
   J.ntr = a.nsweepr / 100;
   J.host_target = (t->d.kind == kTargetHostScalar || t->d.kind == kTargetHostBatched);
@@ -458,6 +474,12 @@ static int rwm_job_finish(RwmJob &J, double *sig_out, double *samples_out, doubl
   cudaFree(J.tr_dev); cudaFree(J.status_dev);
   if (status & 1) return fail(AMX_ETAPE, "injected uniform tape exhausted");
   if (status & 2) return fail(AMX_ENUMERIC, "a chain reached a NaN log-posterior");
+  return AMX_OK;
+}
+
+extern "C" int amx_rwm_set_dof(int student_t_dof) {
+  if (student_t_dof < 0) return fail(AMX_EINVAL, "negative degrees of freedom");
+  g_rwm_dof = student_t_dof;
   return AMX_OK;
 }
 

@@ -285,8 +285,8 @@ static long env_long(const char *name, long dflt) {
 }
 
 static int unsupported_modes(amSampler *am, sampler_ext *e, const char *where) {
-  if (am->student_T_dof > 0 || am->doPerm) {
-    fprintf(stderr, "automix-b200: %s: student_T_dof>0 and doPerm are not built yet (SURVEY.md 8f rank 3)\n", where);
+  if (am->student_T_dof < 0) {
+    fprintf(stderr, "automix-b200: %s: negative student_T_dof\n", where);
     e->stats.last_error = AMX_EINVAL;
     return 1;
   }
@@ -363,6 +363,7 @@ void estimate_conditional_probs(amSampler *am, int nsweep2) {
   }
   {
     double ms = 0.0;
+    amx_rwm_set_dof(am->student_T_dof);
     int rc = amx_rwm_adapt_all(tgt, nsweep2, P, init_all, seed, sig_all, samples_all, tr_sig, tr_acc, &ms);
     e->stats.kernel_ms_rwm += ms;
     free(init_all);
@@ -554,6 +555,7 @@ void burn_samples(amSampler *am, int nburn) {
   if (!am->cpstats.isInitialized) estimate_conditional_probs(am, 100000); /* reference :137-139 */
   if (!am->cpstats.isInitialized || unsupported_modes(am, e, "burn_samples")) return;
   if (report(e, "population setup", ensure_population(am, e, 1))) return;
+  amx_rj_set_modes(e->rj, am->student_T_dof, am->doPerm);
   if (nburn > 0) {
     if (report(e, "amx_rj_sweeps", amx_rj_sweeps(e->rj, nburn, 1, am->doAdapt))) return;
     collect_population(e, am->jd.nmodels);
@@ -602,6 +604,7 @@ void rjmcmc_samples(amSampler *am, int nsweep) {
   st->theta_summary = (double ***)calloc(nm, sizeof(double **));
   e->st_alloc_nsweep = nsweep;
 
+  amx_rj_set_modes(e->rj, am->student_T_dof, am->doPerm);
   if (report(e, "amx_rj_sweeps", amx_rj_sweeps(e->rj, nsweep, 0, am->doAdapt))) return;
   collect_population(e, nm);
   e->stats.sweeps_per_chain = (unsigned long long)nsweep;

@@ -142,6 +142,10 @@ void amx_rj_destroy(amx_rj *rj);
  * (seed, global chain id), so a population sharded over GPUs gives results that do not depend
  * on the number of shards. */
 int amx_rj_set_chain_base(amx_rj *rj, uint64_t first_chain_id);
+/* Optional modes of the sweep (amSampler.student_T_dof, amSampler.doPerm; automix.c:1174-1203): Student-t
+ * innovations with their variable-length gamma rejection draws, and random permutation of the standardised
+ * vector.  Defaults 0 / 0. */
+int amx_rj_set_modes(amx_rj *rj, int student_t_dof, int do_perm);
 /* Parity mode: chain c draws tape[c*stride + i] instead of its Philox stream. */
 int amx_rj_set_tape(amx_rj *rj, const double *tape, long stride);
 /* Start every chain as initChain does (one uniform picks the model). */
@@ -231,6 +235,8 @@ int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long nchains,
                   long tape_stride, double *sig_out, double *samples_out,
                   double *sig_trace0, double *acc_trace0, double *kernel_ms);
 
+/* Student-t proposals for the stage-1 chains started after this call (process-wide, 0 = Gaussian). */
+int amx_rwm_set_dof(int student_t_dof);
 /* Stage 1 for every model at once, the models' kernels overlapping on separate streams.  init_flat,
  * sig_out (nchains x d_k) and samples_out (nchains x 1000 d_k x d_k) are concatenated in model order;
  * sig_trace0 / acc_trace0 are arrays of nmodels pointers (or NULL).  kernel_ms: device time of the stage. */

@@ -241,3 +241,35 @@ def test_host_callback_mode_against_oracle(amx, orc, ht, mode):
         _close(tr2["pk"][c], b["pk"], "pk")
         tot += b["visits"]
     assert np.array_equal(vis.astype(np.int64), tot)
+
+
+@pytest.mark.parametrize("dof,perm", [(5, 0), (0, 1), (3, 1), (1, 0)])
+def test_student_t_and_permutation_modes_against_oracle(amx, orc, ht, dof, perm):
+    """The optional modes of the sweep (student_T_dof, doPerm): the gamma rejection sampler consumes a
+    data-dependent number of uniforms, so a single wrong draw desynchronises everything after it."""
+    wl = cases.workload("toy2")
+    ptr = ht.select(wl["target"])
+    g = cases.load_golden("toy2")
+    mix = _golden_mix(g)
+    dims = np.asarray(wl["dims"])
+    nchains, nsweeps = 16, 80
+    tapes = np.stack([cases.tape(9000 + 31 * c + dof, 4 * cases.rj_tape_len(5, nsweeps)) for c in range(nchains)])
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, nchains, g["init"], n_trace=nchains)
+    pop.set_modes(dof=dof, do_perm=perm)
+    pop.set_tape(tapes)
+    pop.init_chains()
+    pop.sweeps(nsweeps)
+    vis, st = pop.collect()
+    tr = pop.trace()
+    draws = 0
+    for c in range(nchains):
+        orc.tape(tapes[c])
+        s0 = orc.chain_init(dims, g["init"], ptr)
+        r = orc.rj_sweeps(mix, ptr, s0, nsweeps, do_perm=perm, dof=dof)
+        assert not orc.tape_overrun()
+        draws += orc.tape_used()
+        assert np.array_equal(tr["k"][c], r["k"]), (c, "model sequence")
+        _close(tr["lp"][c], r["lp"], "lp", 1e-11)
+        _close(tr["theta"][c], r["theta"], "theta", 1e-11)
+    assert st["draws"] + nchains == draws  # the oracle's count includes the chain-start uniform

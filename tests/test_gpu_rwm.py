@@ -90,3 +90,20 @@ def test_host_callback_mode_against_oracle(amx, orc, ht):
     assert np.array_equal(rep_dev, rep_orc)
     assert _rel(r["samples"][0], o["samples"]) < 1e-9 and _rel(r["sig"][0], o["sig"]) < 1e-9
     assert _rel(r["sig_trace"], o["sig_trace"]) < 1e-9
+
+
+def test_student_t_proposals_against_oracle(amx, orc, ht):
+    wl = cases.workload("toy1")
+    ptr = ht.select(wl["target"])
+    init = cases.default_init(wl, 8)[1:3]
+    tape = cases.tape(777, 3 * cases.rwm_tape_len(2, 1000))
+    T = amx.Target(wl["target"])
+    r = amx.rwm_adapt(T, 1, 1000, 1, init, tapes=tape[None, :], dof=4)
+    orc.tape(tape)
+    o = orc.rwm_within_model(1, 2, 1000, ptr, init, dof=4)
+    assert not orc.tape_overrun()
+    rep_dev = np.all(r["samples"][0][1:] == r["samples"][0][:-1], axis=1)
+    rep_orc = np.all(o["samples"][1:] == o["samples"][:-1], axis=1)
+    assert np.array_equal(rep_dev, rep_orc)
+    assert _rel(r["samples"][0], o["samples"]) < 1e-9 and _rel(r["sig"][0], o["sig"]) < 1e-9
+    amx.rwm_adapt(T, 0, 1000, 1, init[:1], dof=0)  # leave the process-wide setting at its default
