@@ -306,7 +306,7 @@ void estimate_conditional_probs(amSampler *am, int nsweep2) {
     report(e, "plug-in creation", AMX_EINVAL);
     return;
   }
-  if (!cp->isInitialized) { /* same shapes as the reference's initCondProbStats (:254-299) */
+  if (!cp->isInitialized || cp->nfitmix == NULL) { /* same shapes as the reference's initCondProbStats (:254-299) */
     cp->sig_k_rwm_summary = (double ***)calloc(nm, sizeof(double **));
     cp->nacc_ntry_rwm = (double ***)calloc(nm, sizeof(double **));
     cp->nfitmix = (int *)calloc(nm, sizeof(int));
@@ -666,4 +666,82 @@ int amx_sampler_set_seed(amSampler *am, uint64_t seed) {
 const amx_sampler_stats *amx_sampler_stats_get(const amSampler *am) {
   sampler_ext *e = ext_of(am, 0);
   return e ? &e->stats : NULL;
+}
+
+/* ---- proposal distribution on disk --------------------------------------------------
+ * Same token order as the reference's <stem>_mix.data (logwrite.c:247-277: nmodels; the dimensions; per model
+ * the RWM scales, the component count, then per component weight, mean and the lower triangle of B row by
+ * row), so either side reads the other's files -- but written with %.17g, which round-trips a double exactly
+ * (the reference prints %lf, six decimals). */
+int amx_sampler_save_proposal(const amSampler *am, const char *path) {
+  const proposalDist *jd = &am->jd;
+  FILE *f = fopen(path, "w");
+  if (!f) return AMX_EINVAL;
+  fprintf(f, "%d\n", jd->nmodels);
+  for (int k = 0; k < jd->nmodels; k++) fprintf(f, "%d\n", jd->model_dims[k]);
+  for (int k = 0; k < jd->nmodels; k++) {
+    const int d = jd->model_dims[k], L = jd->nMixComps[k];
+    for (int i = 0; i < d; i++) fprintf(f, "%.17g\n", jd->sig[k][i]);
+    fprintf(f, "%d\n", L);
+    for (int l = 0; l < L; l++) {
+      fprintf(f, "%.17g\n", jd->lambda[k][l]);
+      for (int i = 0; i < d; i++) fprintf(f, "%.17g\n", jd->mu[k][l][i]);
+      for (int i = 0; i < d; i++)
+        for (int j = 0; j <= i; j++) fprintf(f, "%.17g\n", jd->B[k][l][i][j]);
+    }
+  }
+  return fclose(f) == 0 ? AMX_OK : AMX_EINVAL;
+}
+
+/* Reads a file in that layout into am->jd with the reference reader's checks (logwrite.c:27-109: model count
+ * and dimensions must match, weights must sum to one within 1e-5 and are renormalised), and marks the
+ * conditional probabilities as estimated so that burn_samples / rjmcmc_samples go straight to stage 3 -- what
+ * the reference's "mode 1" intends but does not do (it forgets the flag and re-estimates). */
+int amx_sampler_load_proposal(amSampler *am, const char *path) {
+  proposalDist *jd = &am->jd;
+  sampler_ext *e = ext_of(am, 1);
+  FILE *f = fopen(path, "r");
+  if (!f) return AMX_EINVAL;
+  int rc = AMX_OK, v = 0;
+  if (fscanf(f, "%d", &v) != 1 || v != jd->nmodels) rc = AMX_EINVAL;
+  for (int k = 0; rc == AMX_OK && k < jd->nmodels; k++)
+    if (fscanf(f, "%d", &v) != 1 || v != jd->model_dims[k]) rc = AMX_EINVAL;
+  for (int k = 0; rc == AMX_OK && k < jd->nmodels; k++) {
+    const int d = jd->model_dims[k];
+    for (int i = 0; i < d && rc == AMX_OK; i++)
+      if (fscanf(f, "%lf", &jd->sig[k][i]) != 1) rc = AMX_EINVAL;
+    int L = 0;
+    if (rc == AMX_OK && (fscanf(f, "%d", &L) != 1 || L < 1 || L > jd->NUM_MIX_COMPS_MAX || L > AMX_MAX_COMPS)) rc = AMX_EINVAL;
+    if (rc != AMX_OK) break;
+    jd->nMixComps[k] = L;
+    double sum = 0.0;
+    for (int l = 0; l < L && rc == AMX_OK; l++) {
+      if (fscanf(f, "%lf", &jd->lambda[k][l]) != 1) rc = AMX_EINVAL;
+      for (int i = 0; i < d && rc == AMX_OK; i++)
+        if (fscanf(f, "%lf", &jd->mu[k][l][i]) != 1) rc = AMX_EINVAL;
+      for (int i = 0; i < d && rc == AMX_OK; i++)
+        for (int j = 0; j <= i && rc == AMX_OK; j++)
+          if (fscanf(f, "%lf", &jd->B[k][l][i][j]) != 1) rc = AMX_EINVAL;
+      sum += jd->lambda[k][l];
+    }
+    if (rc == AMX_OK && fabs(sum - 1.0) > 1E-5) rc = AMX_EINVAL;
+    if (rc == AMX_OK && sum != 1.0)
+      for (int l = 0; l < L; l++) jd->lambda[k][l] /= sum;
+  }
+  fclose(f);
+  if (rc != AMX_OK) {
+    fprintf(stderr, "automix-b200: %s is not a proposal file for this sampler\n", path);
+    e->stats.last_error = rc;
+    return rc;
+  }
+  am->cpstats.isInitialized = true;
+  if (e->rj) { /* a population built on the old proposal is stale */
+    amx_rj_destroy(e->rj);
+    e->rj = NULL;
+  }
+  if (e->prop) {
+    amx_proposal_destroy(e->prop);
+    e->prop = NULL;
+  }
+  return AMX_OK;
 }

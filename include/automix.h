@@ -198,6 +198,11 @@ int amx_sampler_set_chains(amSampler *am, long rj_chains, long rwm_chains);
  * from the clock as the reference does). */
 int amx_sampler_set_seed(amSampler *am, uint64_t seed);
 const amx_sampler_stats *amx_sampler_stats_get(const amSampler *am);
+/* The fitted proposal distribution (am->jd) on disk, in the token order of the reference's <stem>_mix.data
+ * (logwrite.c:247-277) but lossless (%.17g).  Loading marks the conditional probabilities as estimated, so
+ * burn_samples / rjmcmc_samples skip stages 1-2 (the intent of the reference's mode 1). */
+int amx_sampler_save_proposal(const amSampler *am, const char *path);
+int amx_sampler_load_proposal(amSampler *am, const char *path);
 
 #ifdef __cplusplus
 }

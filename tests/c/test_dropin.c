@@ -161,6 +161,26 @@ static void test_device_plugin(void) {
   CHECK(s->last_error == 0, "GPU stage failed: %s", amx_last_error());
   CHECK(fabs(p0 - 0.3) < 0.01, "posterior model probability");
   CHECK(am.jd.nMixComps[0] >= 1 && am.jd.nMixComps[1] >= 2, "mixture fit");
+  /* the fitted proposal on disk, and a second sampler that starts from it: stages 1-2 are skipped */
+  CHECK(amx_sampler_save_proposal(&am, "/tmp/amx_toy1_mix.data") == 0, "save proposal");
+  amSampler am2;
+  initAMSampler(&am2, 2, dims, NULL, init);
+  amx_sampler_set_target(&am2, t);
+  amx_sampler_set_seed(&am2, 100);
+  amx_sampler_set_chains(&am2, 32768, 1);
+  CHECK(amx_sampler_load_proposal(&am2, "/tmp/amx_toy1_mix.data") == 0, "load proposal");
+  am2.student_T_dof = 5; /* optional modes through the reference's own fields */
+  am2.doPerm = 1;
+  burn_samples(&am2, 500);
+  rjmcmc_samples(&am2, 1500);
+  const amx_sampler_stats *s2 = amx_sampler_stats_get(&am2);
+  double q0 = s2->visits[0] / (double)(s2->visits[0] + s2->visits[1]);
+  printf("  from the saved proposal, Student-t(5) + permutation: P(model 1) = %.4f, stage-1/2 kernel time %.1f ms\n", q0,
+         s2->kernel_ms_rwm + s2->kernel_ms_em);
+  CHECK(s2->last_error == 0 && fabs(q0 - 0.3) < 0.012, "posterior model probability from a loaded proposal");
+  CHECK(s2->kernel_ms_rwm == 0.0 && s2->kernel_ms_em == 0.0, "stages 1-2 were skipped");
+  CHECK(am2.jd.lambda[1][0] == am.jd.lambda[1][0] && am2.jd.B[1][0][1][0] == am.jd.B[1][0][1][0], "proposal survived the file bit for bit");
+  freeAMSampler(&am2);
   freeAMSampler(&am);
   amx_target_destroy(t);
 }

@@ -38,3 +38,17 @@ def test_dropin_pipelines():
     print(r.stdout[-4000:])
     print(r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_proposal_file_round_trip(tmp_path):
+    """CPU-only: lossless save/load of the proposal distribution in the reference's _mix.data layout."""
+    from automix_b200 import build
+
+    build.build()
+    exe = os.path.join(ROOT, "tests", "c", "test_proposal_io")
+    lib = os.path.join(ROOT, "automix_b200", "lib")
+    subprocess.run([os.environ.get("CC", "gcc"), "-O2", "-Wall", os.path.join(ROOT, "tests", "c", "test_proposal_io.c"),
+                    "-I", os.path.join(ROOT, "include"), "-L", lib, "-lautomix", "-lm", "-Wl,-rpath," + lib, "-o", exe],
+                   check=True)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
