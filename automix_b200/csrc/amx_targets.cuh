@@ -121,7 +121,8 @@ struct QuadTarget {
 };
 
 // ---- coal-mining change-point posterior (usercpt.c:46-134) ------------------------------
-__constant__ double c_coal_y[AMX_COAL_N] = {AMX_COAL_VALUES};
+__constant__ double c_coal_y[AMX_COAL_N] = {AMX_COAL_VALUES};   // uniform index across lanes: the sequential walk
+__device__ const double g_coal_y[AMX_COAL_N] = {AMX_COAL_VALUES};  // divergent index: the binary searches
 
 struct CoalTarget {
   // blob: amx_fam_hdr (dims only) + per model [c_prior, c_tail]: the two log-gamma
@@ -160,6 +161,31 @@ struct CoalTarget {
         lp += log(ds[i]);
       }
       lp += D[h->off[k] + 1];
+      // Likelihood.  The reference walks the 191 sorted data once and lets the segment index advance by at
+      // most one per datum (usercpt.c:114-127).  If every change point is followed by a datum of its own
+      // segment -- first index beyond s_m strictly increasing in m and below 191 -- that walk visits the
+      // segments exactly at those indices and its sum is  sum_j (idx_{j+1}-idx_j) log h_j - h_j ds_j  with the
+      // same terms in the same order, so ns binary searches replace the 191-step walk.  Otherwise (two change
+      // points in one data gap, or none of the data beyond one) the walk's late advances matter: fall back.
+      int idx[9];
+      idx[0] = 0;
+      bool regular = true;
+      for (int m = 1; m <= ns; m++) {
+        int lo = 0, hi = AMX_COAL_N;  // first i with y[i] > s[m]
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (g_coal_y[mid] > s[m]) hi = mid;
+          else lo = mid + 1;
+        }
+        idx[m] = lo;
+        regular &= (lo > idx[m - 1] || m == 1) && (lo < AMX_COAL_N);
+      }
+      if (regular) {
+        idx[ns + 1] = AMX_COAL_N;
+        double llh = 0.0;
+        for (int j = 0; j <= ns; j++) llh += ((idx[j + 1] - idx[j]) * log(hh[j]) - hh[j] * ds[j]);
+        return lp + llh;
+      }
       int seen = 0, j = 0;
       double top = s[1], llh = 0.0;
       for (int i = 0; i < AMX_COAL_N; i++) {

@@ -34,3 +34,45 @@ def test_plugin_matches_host_callback(amx, ht, name):
     assert np.array_equal(np.isfinite(got), fin)
     err = np.abs(got[fin] - want[fin]) / np.maximum(1.0, np.abs(want[fin]))
     assert err.max() < 1e-12, err.max()
+
+
+def test_coalmine_fast_path_and_walk_agree_with_the_reference_walk(amx, ht):
+    """The device plug-in replaces the 191-step data walk by binary searches when that is exactly equivalent,
+    and keeps the walk otherwise (two change points inside one data gap, change points beyond the last datum,
+    before the first one).  The host callback always walks, as usercpt.c does."""
+    wl = cases.workload("coalmine")
+    ht.select(wl["target"])
+    T = amx.Target(wl["target"])
+    rng = np.random.default_rng(11)
+    y = np.array([74.0, 231, 354, 356, 480, 492, 40623])
+    ks, xs = [], []
+    for trial in range(3000):
+        k = int(rng.integers(0, 6))
+        ns = k + 1
+        h = rng.random(ns + 1) * 0.02 + 1e-4
+        mode = trial % 5
+        if mode == 0:    # generic positions
+            s = np.sort(rng.random(ns) * 40907.0)
+        elif mode == 1:  # several change points inside one data gap (1145 .. 1971, 36673 .. 39039)
+            lo, hi = ((1146.0, 1970.0), (36674.0, 39038.0))[trial % 2]
+            s = np.sort(lo + rng.random(ns) * (hi - lo))
+        elif mode == 2:  # beyond the last datum
+            s = np.sort(40624.0 + rng.random(ns) * 280.0)
+        elif mode == 3:  # before the first datum / on top of data values
+            s = np.sort(np.concatenate([rng.random(1) * 74.0, rng.choice(y, ns - 1) + rng.integers(0, 2, ns - 1)]))[:ns] if ns > 1 else rng.random(1) * 74.0
+            s = np.sort(s + np.arange(ns) * 1e-3)
+        else:            # clustered
+            c = rng.random() * 40000.0
+            s = np.sort(c + rng.random(ns) * 300.0)
+        x = np.zeros(13)
+        x[: ns + 1] = h
+        x[ns + 1: 2 * ns + 1] = s
+        ks.append(k)
+        xs.append(x)
+    ks = np.array(ks, np.int32)
+    xs = np.array(xs)
+    got = T.eval(ks, xs)
+    dims = wl["dims"]
+    want = np.array([ht.logpost(int(k), x[: dims[k]].copy()) for k, x in zip(ks, xs)])
+    err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
+    assert err.max() < 1e-12, (err.max(), int(err.argmax()))
