@@ -82,6 +82,7 @@ struct EmPublic {
   int slot[kEmLmax];
   double lam[kEmLmax];
   double rec[kEmRecMax];
+  double pivot[kEmDmax];  // current mean of component `next`: the shift of the fused second moments
 };
 
 // The per-GPU pieces of a sample-sharded fit.  All pointers are valid on every participating GPU (peer
@@ -101,6 +102,8 @@ struct EmArgs {
   const double *init_rows;  // [Lmax][d] the data rows that start the components (on GPU 0)
   EmDev dev[kEmMaxDev];
   int d, Lmax, maxit;
+  int fused;    // 1: the refresh pass also accumulates the (pivot-shifted) second moments of the next component,
+                // so a component step is ONE pass and ONE barrier; 0: separate centred scatter pass
   int use_tma;  // 1: tile rows by cp.async.bulk + mbarrier; 0: coalesced per-thread loads into the tile
   int nbuf;  // tile buffers per CTA: 2 = fetch of tile k+1 overlaps tile k, 1 = more resident CTAs
   long n, npad;
@@ -195,6 +198,7 @@ __device__ __forceinline__ void barrier_release(const EmArgs &a, int d, unsigned
       __stcg(&p->lam[threadIdx.x], ld_cg(&c->lam[threadIdx.x]));
     }
     for (int q = threadIdx.x; q < reclen; q += blockDim.x) __stcg(&p->rec[q], ld_cg(&c->rec[q]));
+    if (threadIdx.x < d) __stcg(&p->pivot[threadIdx.x], ld_cg(&c->mu[ld_cg(&c->next)][threadIdx.x]));
   }
   if (a.ndev > 1) __threadfence_system();
   else __threadfence();
@@ -305,6 +309,8 @@ struct LeaderS {
   int slot[kEmLmax];
   double lam[kEmLmax], colsum[kEmLmax], S1[kEmLmax], tmp[kEmLmax];
   double Bc[DMAX * (DMAX + 1) / 2];
+  double S2[DMAX * (DMAX + 1) / 2];  // fused mode: shifted second moments of the component about to be updated
+  double dl[DMAX];                   // fused mode: mean shift S1 / S0
   int chol_ok;
 };
 
@@ -500,6 +506,8 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
     // a refresh finished: s_tot = [colsum (Lmax) | loglik | fallbacks | S1 (d)]
     if (t < S.L) S.colsum[t] = s_tot[t];
     if (t < d) S.S1[t] = s_tot[kEmLmax + 2 + t];
+    if (a.fused)
+      for (int q = t; q < tri; q += blockDim.x) S.S2[q] = s_tot[kEmLmax + 2 + d + q];
     if (t == 0) {
       S.loglik = s_tot[kEmLmax] - 500.0 * s_tot[kEmLmax + 1];
       if (S.iters == 0) {  // initial E-step done: start outer iteration 1
@@ -539,7 +547,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
         }
         __syncthreads();
         leader_renorm<DMAX>(S);
-        if (S.lam[cc] > 0.005) {  // uniform branch (shared value)
+        if (S.lam[cc] > 0.005 && !a.fused) {  // uniform branch (shared value)
           if (t < d) {
             const double m = S.S1[t] / S.colsum[cc];
             c->mu[cc][t] = m;
@@ -547,6 +555,42 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
           }
           if (t == 0) {
             S.pass = kPassScatter;
+            S.act = kActDone;
+          }
+        } else if (S.lam[cc] > 0.005) {
+          // fused: S1, S2 are moments of (x - pivot), pivot = the component's mean before this update.
+          //   mean = pivot + S1/S0,   cov = S2/S0 - (S1/S0)(S1/S0)^T   (:797-810 in shifted form)
+          const double S0 = S.colsum[cc];
+          if (t < d) {
+            S.dl[t] = S.S1[t] / S0;
+            c->mu[cc][t] = ld_cg(&c->mu[cc][t]) + S.dl[t];
+          }
+          __syncthreads();
+          for (int q = t; q < tri; q += blockDim.x) {
+            int j = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+            while ((j + 1) * (j + 2) / 2 <= q) j++;
+            while (j * (j + 1) / 2 > q) j--;
+            const int k = q - j * (j + 1) / 2;
+            S.Bc[q] = (S.S2[q] - S.S1[j] * S.dl[k]) / S0;
+          }
+          __syncthreads();
+          if (t < 32) {
+            const bool ok = warp_chol<DMAX>(S.Bc, d);
+            if (t == 0) S.chol_ok = ok ? 1 : 0;
+          }
+          __threadfence();
+          __syncthreads();
+          for (int q = t; q < tri; q += blockDim.x) c->B[cc][q] = S.Bc[q];
+          leader_make_rec<DMAX>(c, S, d, cc);
+          if (t == 0) {
+            if (!S.chol_ok) {
+              S.status = AMX_ENUMERIC;
+              S.stop = 1;
+              S.pass = kPassStop;
+            } else {
+              S.next = (cc + 1 < S.L) ? cc + 1 : 0;
+              S.pass = kPassDensRefresh;
+            }
             S.act = kActDone;
           }
         } else {  // natural annihilation (:821-845): refresh before the next component is looked at
@@ -703,14 +747,19 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
   constexpr int RSPLIT = DMAX > 8 ? 8 : DMAX;  // DMAX > 8: two row groups, [0,8) and [8,DMAX)
   extern __shared__ __align__(16) double tile[];
   __shared__ __align__(8) uint64_t s_bar[4];  // one mbarrier per tile buffer / pipeline stage
-  __shared__ double s_red[kEmWarps * NRED];
-  __shared__ double s_tot[NRED > kEmLmax + 2 + DMAX ? NRED : kEmLmax + 2 + DMAX];
-  __shared__ double s_chunk[8 * (NRED > kEmLmax + 2 + DMAX ? NRED : kEmLmax + 2 + DMAX)];
+  // The reduction scratch, the leader's totals and the leader's state are only live while the tile is idle
+  // (end of a pass, barrier, leader section), so they alias the tile memory instead of adding ~7 KB of static
+  // shared memory per CTA (which would cost a resident CTA per SM).
+  constexpr int NTOT = kEmLmax + 2 + DMAX + TRI;
+  double *s_red = tile;                         // [kEmWarps * NRED]
+  double *s_tot = tile + kEmWarps * NRED;       // [NTOT]
+  double *s_chunk = nullptr;
+  LeaderS<DMAX> &s_lead = *reinterpret_cast<LeaderS<DMAX> *>(tile + kEmWarps * NRED + NTOT + (NTOT & 1));
+  __shared__ double s_pivot[DMAX];
   __shared__ double s_rec[AMX_REC_HEAD + 2 * DMAX + TRI];
   __shared__ double s_lam[kEmLmax];
   __shared__ int s_slot[kEmLmax];
   __shared__ int s_pass, s_L, s_c, s_next;
-  __shared__ LeaderS<DMAX> s_lead;
 
   EmCtrl *ctrl = a.ctrl;
   const int d = a.d;
@@ -719,7 +768,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
   const long stride = (long)gridDim.x * blockDim.x;
   const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int tile_doubles = (d + a.Lmax + 1) * kEmTS;  // two such buffers: fetch of tile k+1 overlaps tile k
+  const int tile_doubles = (d + a.Lmax + 1 + (a.fused ? d : 0)) * kEmTS;  // rows: x | E | w_next | (w_next * dx)
   double *part_col = a.dev[a.rank].part + blockIdx.x;  // value q of this CTA lives at part_col[q * gridDim.x]
   const size_t pstride = gridDim.x;
   unsigned epoch = 0;
@@ -923,6 +972,19 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
       const int cslot = dens ? s_slot[cc] : 0;
       const int col = t >> 2, prt = t & 3;  // reduction role: 32 columns x 4 partial sums
       double acc_col = 0.0, acc_s1 = 0.0, ll = 0.0, nfb = 0.0;
+      // fused mode: thread (half, e) owns triangle entries e, e+64 over the samples of its half of the tile
+      const int tri_d = d * (d + 1) / 2, half = t >> 6;
+      double acc2[2] = {0.0, 0.0};
+      int ej[2] = {0, 0}, ek[2] = {0, 0};
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const int e = (t & 63) + 64 * q;
+        int j = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while ((j + 1) * (j + 2) / 2 <= e) j++;
+        while (j * (j + 1) / 2 > e) j--;
+        ej[q] = j;
+        ek[q] = e - j * (j + 1) / 2;
+      }
       auto fetch = [&](long tl, int bf) {  // warp 0: one bulk copy per tile row, lanes in parallel
         double *xs = tile + bf * tile_doubles, *Es = xs + d * kEmTS;
         fence_proxy_async();
@@ -1017,7 +1079,18 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         }
         const double wn = Es[nx * kEmTS + t];
         ws[t] = wn;
-        if (valid) __stcg(a.wnxt + i, wn);
+        if (a.fused) {  // shift by the pivot: the rows become dx = x - pivot and w_next * dx
+          double *wd = ws + kEmTS;
+#pragma unroll
+          for (int j = 0; j < DMAX; j++)
+            if (j < d) {
+              const double dxj = xs[j * kEmTS + t] - s_pivot[j];
+              xs[j * kEmTS + t] = dxj;
+              wd[j * kEmTS + t] = wn * dxj;
+            }
+        } else if (valid) {
+          __stcg(a.wnxt + i, wn);
+        }
         __syncthreads();
         // -- reduction phase: thread (col, prt) sums every 4th sample of column col
         if (col < L) {
@@ -1032,9 +1105,22 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
           for (int k = 0; k < kEmThreads / 4; k++) s4 = fma(ws[prt + 4 * k], xs[col * kEmTS + prt + 4 * k], s4);
           acc_s1 += s4;
         }
+        if (a.fused) {
+          const double *wd = ws + kEmTS;
+#pragma unroll
+          for (int q = 0; q < 2; q++) {
+            if ((t & 63) + 64 * q < tri_d) {
+              const double *pa = wd + ej[q] * kEmTS + 64 * half, *pb = xs + ek[q] * kEmTS + 64 * half;
+              double s2 = 0.0;
+#pragma unroll 8
+              for (int k = 0; k < 64; k++) s2 = fma(pa[k], pb[k], s2);
+              acc2[q] += s2;
+            }
+          }
+        }
         __syncthreads();
       }
-      // partial row: [colsum (Lmax) | loglik | fallbacks | S1 (d)]
+      // partial row: [colsum (Lmax) | loglik | fallbacks | S1 (d) | S2 (tri, fused mode)]
       acc_col += __shfl_xor_sync(0xffffffffu, acc_col, 1);
       acc_col += __shfl_xor_sync(0xffffffffu, acc_col, 2);
       acc_s1 += __shfl_xor_sync(0xffffffffu, acc_s1, 1);
@@ -1056,6 +1142,18 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         part_col[(size_t)(kEmLmax + t) * pstride] = tot;
       }
       nv = kEmLmax + 2 + d;
+      if (a.fused) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+          const int e = (t & 63) + 64 * q;
+          if (e < tri_d) s_red[half * NRED + e] = acc2[q];
+        }
+        __syncthreads();
+        for (int e = t; e < tri_d; e += blockDim.x)
+          part_col[(size_t)(kEmLmax + 2 + d + e) * pstride] = s_red[e] + s_red[NRED + e];
+        nv += tri_d;
+      }
     }
 
     // ------------------------------------------------------------------ barrier + leader
@@ -1100,6 +1198,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
     }
     const int reclen = AMX_REC_HEAD + 2 * d + d * (d + 1) / 2;
     for (int q = threadIdx.x; q < reclen; q += blockDim.x) s_rec[q] = ld_cg(&pub->rec[q]);
+    if (threadIdx.x < DMAX) s_pivot[threadIdx.x] = (threadIdx.x < d) ? ld_cg(&pub->pivot[threadIdx.x]) : 0.0;
     __syncthreads();
     pass = s_pass;
     if (threadIdx.x == 0 && blockIdx.x == 0 && a.rank == 0) atomicAdd((unsigned long long *)&ctrl->dbg[5], (unsigned long long)(clock64() - tk2));
@@ -1233,7 +1332,10 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   const char *nb = getenv("AMX_EM_NBUF"), *tm = getenv("AMX_EM_TMA");
   const int use_tma = tm ? (atoi(tm) != 0) : 1;  // measured on B200 (n=1e6, d=10, L=30): TMA 183 us/step, plain loads 244
   const int nbuf = (use_tma && nb && atoi(nb) == 2) ? 2 : 1;
-  const size_t smem = nbuf * sizeof(double) * (size_t)(d + Lmax + 1) * kEmTS;
+  const char *fu = getenv("AMX_EM_FUSED");
+  const int fused = (d <= 12 && use_tma && nbuf == 1) ? (fu ? (atoi(fu) != 0) : 1) : 0;  // entries e, e+64 cover tri(12) = 78
+  size_t smem = nbuf * sizeof(double) * (size_t)(d + Lmax + 1 + (fused ? d : 0)) * kEmTS;
+  if (smem < 24 * 1024) smem = 24 * 1024;  // room for the leader's state, which aliases the tile
 
   EmArgs A[kEmMaxDev];
   cudaStream_t st[kEmMaxDev];
@@ -1299,6 +1401,7 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     a.maxit = maxit;
     a.use_tma = use_tma;
     a.nbuf = nbuf;
+    a.fused = fused;
     a.n = off[g + 1] - off[g];
     a.npad = (a.n + kEmThreads - 1) / kEmThreads * kEmThreads;  // whole tiles; the padding is zero and carries no weight
     a.ctrl = ctrl;
