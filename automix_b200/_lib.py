@@ -45,9 +45,19 @@ EXPORTS = [
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
     "amx_rj_set_tape", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
-    "amx_rj_collect", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_em_fit", "amx_em_fit_dev",
+    "amx_rj_collect", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_sokal", "amx_sokal_dev", "amx_rj_sokal",
+    "amx_rj_moments_reset", "amx_rj_moments_accumulate", "amx_rj_moments_get", "amx_em_fit", "amx_em_fit_dev",
     "amx_em_draw_init", "amx_em_fit_multi", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
 ]
+
+
+def sokal(x):
+    """Sokal integrated autocorrelation time of each row of ``x`` ([nseries, n] or [n]); see amx_sokal."""
+    x = np.atleast_2d(f64(x))
+    ns, n = x.shape
+    var, tau, m = np.zeros(ns), np.zeros(ns), np.zeros(ns, np.int32)
+    check(lib().amx_sokal(ns, n, _d(x), _d(var), _d(tau), _i(m)))
+    return var, tau, m
 
 
 def lib():
@@ -93,6 +103,12 @@ def lib():
     L.amx_rj_sweeps.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int]
     L.amx_rj_collect.argtypes = [C.c_void_p, _u64p, C.POINTER(RjStats), C.c_int]
     L.amx_rj_get_trace.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp]
+    L.amx_sokal.argtypes = [C.c_int, C.c_long, _dp, _dp, _dp, _ip]
+    L.amx_sokal_dev.argtypes = [C.c_int, C.c_long, C.c_void_p, _dp, _dp, _ip]
+    L.amx_rj_sokal.argtypes = [C.c_void_p, C.c_long, _dp, _dp, _ip]
+    L.amx_rj_moments_reset.argtypes = [C.c_void_p]
+    L.amx_rj_moments_accumulate.argtypes = [C.c_void_p]
+    L.amx_rj_moments_get.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong), _dp, _dp, _dp]
     L.amx_rj_visits_dev.restype = C.c_void_p
     L.amx_rj_visits_dev.argtypes = [C.c_void_p]
     if hasattr(L, "amx_em_fit"):
@@ -325,6 +341,25 @@ class RjPopulation:
 
     def visits_dev_ptr(self) -> int:
         return int(lib().amx_rj_visits_dev(self.h))
+
+    # -- posterior summaries on the device ----------------------------------------------------
+    def sokal(self, nkeep: int):
+        """(var, tau, m) per trace chain over the last ``nkeep`` sweeps of the last sweeps call."""
+        var, tau, m = np.zeros(self.n_trace), np.zeros(self.n_trace), np.zeros(self.n_trace, np.int32)
+        check(lib().amx_rj_sokal(self.h, int(nkeep), _d(var), _d(tau), _i(m)))
+        return var, tau, m
+
+    def moments_reset(self):
+        check(lib().amx_rj_moments_reset(self.h))
+
+    def moments_accumulate(self):
+        check(lib().amx_rj_moments_accumulate(self.h))
+
+    def moments(self, model: int, d: int):
+        cnt = C.c_ulonglong()
+        mean, cov, mlp = np.zeros(d), np.zeros((d, d)), C.c_double()
+        check(lib().amx_rj_moments_get(self.h, int(model), C.byref(cnt), _d(mean), _d(cov), C.byref(mlp)))
+        return dict(count=int(cnt.value), mean=mean, cov=cov, mean_lp=mlp.value)
 
     def close(self):
         if self.h:

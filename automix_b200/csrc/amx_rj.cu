@@ -454,6 +454,7 @@ struct amx_rj {
   cudaEvent_t e0, e1;
   double kernel_ms;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *pending;
+  MomentsBuf *mom;    // posterior-moment accumulators (amx_summary.cu), created on first use
   double *stage_dev;  // chain-major staging for set/get_state
   long stage_cap;
   // host-callback mode
@@ -696,6 +697,7 @@ void amx_rj_destroy(amx_rj *rj) {
     cudaEventDestroy(pr.second);
   }
   delete rj->pending;
+  moments_free(rj->mom);
   cudaFree(rj->stage_dev);
   cudaFree(rj->sp.thn); cudaFree(rj->sp.keval); cudaFree(rj->sp.lpn); cudaFree(rj->sp.kn); cudaFree(rj->sp.carry);
   if (rj->h_thn) cudaFreeHost(rj->h_thn);
@@ -705,6 +707,30 @@ void amx_rj_destroy(amx_rj *rj) {
   delete rj->h_xc;
   delete rj->h_lc;
   delete rj;
+}
+
+// ---- posterior summaries (kernels in amx_summary.cu) ------------------------------------------------
+int amx_rj_moments_reset(amx_rj *rj) {
+  if (!rj) return fail(AMX_EINVAL, "null population");
+  return moments_reset(&rj->mom, rj->prop->hdr);
+}
+
+int amx_rj_moments_accumulate(amx_rj *rj) {
+  if (!rj) return fail(AMX_EINVAL, "null population");
+  if (!rj->mom)
+    if (int rc = moments_reset(&rj->mom, rj->prop->hdr)) return rc;
+  return moments_accumulate(rj->mom, rj->st.k, rj->st.theta, rj->st.lp, rj->C, rj->dmax, rj->prop->blob_dev);
+}
+
+int amx_rj_moments_get(const amx_rj *rj, int model, unsigned long long *count, double *mean, double *cov,
+                       double *mean_lp) {
+  if (!rj || !rj->mom) return fail(AMX_EINVAL, "no moments accumulated");
+  return moments_get(rj->mom, rj->prop, model, count, mean, cov, mean_lp);
+}
+
+int amx_rj_sokal(const amx_rj *rj, long nkeep, double *var, double *tau, int *m) {
+  if (!rj || rj->ntrace < 1 || rj->last_nsweeps < 1) return fail(AMX_EINVAL, "no trace recorded");
+  return sokal_ktrace(rj->tr_k, rj->last_nsweeps, nkeep, rj->ntrace, var, tau, m);
 }
 
 int amx_rj_set_modes(amx_rj *rj, int student_t_dof, int do_perm) {

@@ -634,6 +634,14 @@ void rjmcmc_samples(amSampler *am, int nsweep) {
   free(tk);
   free(tlp);
   free(tth);
+  /* Posterior summaries, computed where the data is.  The reference leaves var/tau/m to its report writer
+   * (sokal(st.nkeep, st.xr, ...), logwrite.c:228); the same numbers are filled in here, from the same xr
+   * (its last entry is never written by the reference's loop, :122-124; it is zero here), without
+   * overwriting xr as sokal() does.  The population's final states give one posterior draw per chain:
+   * their per-model moments are kept for amx_sampler_posterior. */
+  if (st->nkeep >= 4) report(e, "amx_sokal", amx_sokal(1, st->nkeep, st->xr, &st->var, &st->tau, &st->m));
+  if (!report(e, "amx_rj_moments_reset", amx_rj_moments_reset(e->rj)))
+    report(e, "amx_rj_moments_accumulate", amx_rj_moments_accumulate(e->rj));
   /* acceptance counters: population totals (64-bit fields) */
   st->naccrwmb = e->stats.acc_block;
   st->ntryrwmb = e->stats.try_block;
@@ -662,6 +670,12 @@ int amx_sampler_set_seed(amSampler *am, uint64_t seed) {
   e->seed = seed;
   e->seed_set = 1;
   return AMX_OK;
+}
+int amx_sampler_posterior(const amSampler *am, int model, unsigned long long *count, double *mean, double *cov,
+                          double *mean_lp) {
+  sampler_ext *e = ext_of(am, 0);
+  if (!e || !e->rj) return AMX_EINVAL;
+  return amx_rj_moments_get(e->rj, model, count, mean, cov, mean_lp);
 }
 const amx_sampler_stats *amx_sampler_stats_get(const amSampler *am) {
   sampler_ext *e = ext_of(am, 0);

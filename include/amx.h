@@ -175,6 +175,31 @@ int amx_rj_get_trace(const amx_rj *rj, int *k, double *lp, double *theta,
  * that never leaves HBM). */
 void *amx_rj_visits_dev(amx_rj *rj);
 
+/* ---- posterior summaries on the device (what users form from runStats) ---- */
+/* Integrated autocorrelation time by Sokal's adaptive truncated periodogram, the computation of
+ * the reference's report writer (user_examples/logwrite.c:354-403: sokal(n, xr, &var, &tau, &m)
+ * over the model-index series recorded at automix.c:122-124), for nseries independent series of
+ * length n each (x: [nseries][n], a power of two in [4, 2^20] as the reference requires).
+ * Outputs per series: var (sample variance), tau (the reference's convention: twice Sokal's),
+ * m (window length + 1; n + 1 when the window never closes; tau is NaN for a constant series,
+ * as with the reference).  The input is not modified (the reference overwrites it). */
+int amx_sokal(int nseries, long n, const double *x, double *var, double *tau, int *m);
+int amx_sokal_dev(int nseries, long n, const double *x_dev, double *var, double *tau, int *m);
+/* The same over the model-index series of the population's trace chains: the last nkeep sweeps
+ * of the last amx_rj_sweeps call, one (var, tau, m) per trace chain; nothing leaves the device
+ * but the results. */
+int amx_rj_sokal(const amx_rj *rj, long nkeep, double *var, double *tau, int *m);
+/* Per-model posterior moments over the population (the means/covariances a user computes from
+ * runStats.theta_summary, automix.c:105-120, without materialising per-sweep rows):
+ * _accumulate adds the population's CURRENT states (one draw per chain) to running totals, so a
+ * caller alternates amx_rj_sweeps(thin) and _accumulate; _get returns for one model the number
+ * of draws, their mean[d], unbiased covariance cov[d*d] and mean log-posterior (any may be NULL).
+ * Reduction order is fixed: results are bitwise reproducible. */
+int amx_rj_moments_reset(amx_rj *rj);
+int amx_rj_moments_accumulate(amx_rj *rj);
+int amx_rj_moments_get(const amx_rj *rj, int model, unsigned long long *count, double *mean,
+                       double *cov, double *mean_lp);
+
 /* ---- K2: Figueiredo-Jain component-wise EM mixture fit ------------------- */
 /* Replaces fit_mixture_from_samples (:664-1006) and fit_autorj (:1008-1033). */
 typedef struct amx_em_result {

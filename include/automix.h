@@ -198,6 +198,12 @@ int amx_sampler_set_chains(amSampler *am, long rj_chains, long rwm_chains);
  * from the clock as the reference does). */
 int amx_sampler_set_seed(amSampler *am, uint64_t seed);
 const amx_sampler_stats *amx_sampler_stats_get(const amSampler *am);
+/* Per-model posterior moments over the population after rjmcmc_samples: one draw per chain (its final
+ * state); count = chains in that model, mean[d], unbiased cov[d*d], mean log-posterior (any may be NULL).
+ * rjmcmc_samples also fills am->st.var / tau / m with Sokal's integrated autocorrelation time of chain 0's
+ * model-index series am->st.xr -- the numbers the reference's report writer prints (logwrite.c:228, :327). */
+int amx_sampler_posterior(const amSampler *am, int model, unsigned long long *count, double *mean, double *cov,
+                          double *mean_lp);
 /* The fitted proposal distribution (am->jd) on disk, in the token order of the reference's <stem>_mix.data
  * (logwrite.c:247-277) but lossless (%.17g).  Loading marks the conditional probabilities as estimated, so
  * burn_samples / rjmcmc_samples skip stages 1-2 (the intent of the reference's mode 1). */

@@ -898,3 +898,89 @@ void orc_mix_logpdf(int d, int L, const double *lam, const double *mu,
     if (mix) mix[i] = log(s);
   }
 }
+
+/* ---- posterior summaries -------------------------------------------------
+ * Integrated autocorrelation time by Sokal's adaptive truncated periodogram, as the reference's
+ * report writer computes it for the model-index series (user_examples/logwrite.c:354-403):
+ *   1. forward DFT of x, power spectrum, DC term set to zero (= remove the mean) (:369-377);
+ *   2. a second forward DFT turns the spectrum into n * circular autocovariance (:379);
+ *      var = acov[0] / (n (n-1)) (:380), rho[t] = acov[t] / acov[0] (:381-385);
+ *   3. window: sum = -1/3; for i = 0..n-1: sum += rho[i] - 1/6, stop at the first sum < 0;
+ *      tau = 2 (sum + i/6), m = i + 1 (:390-401) -- twice Sokal's definition, and with i = n,
+ *      m = n + 1 when the sum never turns negative (a constant series gives NaN and lands there).
+ * The reference's transform is a radix-4 routine (:405-651); a DFT is a DFT, so this restatement
+ * uses a plain iterative radix-2 one.  Results agree to rounding (1e-10 relative in the tests,
+ * m exactly).  n must be a power of two >= 4 (the reference prints a message and returns
+ * otherwise, :424-439). */
+static void orc_fft_pow2(long n, double *re, double *im) {
+  for (long i = 1, j = 0; i < n; i++) {
+    long bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      double t = re[i]; re[i] = re[j]; re[j] = t;
+      t = im[i]; im[i] = im[j]; im[j] = t;
+    }
+  }
+  for (long len = 2; len <= n; len <<= 1) {
+    long half = len >> 1;
+    for (long k = 0; k < half; k++) {
+      double ang = -6.283185307179586476925 * (double)k / (double)len;
+      double wr = cos(ang), wi = sin(ang);
+      for (long s = k; s < n; s += len) {
+        long q = s + half;
+        double tr = re[q] * wr - im[q] * wi, ti = re[q] * wi + im[q] * wr;
+        re[q] = re[s] - tr; im[q] = im[s] - ti;
+        re[s] += tr; im[s] += ti;
+      }
+    }
+  }
+}
+
+int orc_sokal(long n, const double *x, double *var, double *tau, int *m) {
+  if (n < 4 || (n & (n - 1)) || n > (1L << 20)) return -1;
+  double *re = (double *)malloc(sizeof(double) * n), *im = (double *)calloc(n, sizeof(double));
+  for (long i = 0; i < n; i++) re[i] = x[i];
+  orc_fft_pow2(n, re, im);
+  for (long i = 0; i < n; i++) {
+    re[i] = re[i] * re[i] + im[i] * im[i];
+    im[i] = 0.0;
+  }
+  re[0] = 0.0;
+  orc_fft_pow2(n, re, im);
+  *var = re[0] / ((double)n * (double)(n - 1));
+  double c = 1.0 / re[0], sum = -(1.0 / 3.0);
+  long i;
+  for (i = 0; i < n; i++) {
+    sum += re[i] * c - (1.0 / 6.0);
+    if (sum < 0.0) break;
+  }
+  *tau = 2.0 * (sum + (double)i / 6.0);
+  *m = (int)i + 1;
+  free(re);
+  free(im);
+  return 0;
+}
+
+/* Per-model posterior moments of a set of draws (what a user forms from runStats.theta_summary,
+ * automix.c:105-120): count, mean and unbiased covariance of the rows with k[i] == model. */
+long orc_model_moments(long n, int dmax, const int *k, const double *theta, int model, int d,
+                       double *mean, double *cov) {
+  long cnt = 0;
+  for (int j = 0; j < d; j++) mean[j] = 0.0;
+  for (long i = 0; i < n; i++)
+    if (k[i] == model) {
+      cnt++;
+      for (int j = 0; j < d; j++) mean[j] += theta[i * dmax + j];
+    }
+  if (cnt == 0) return 0;
+  for (int j = 0; j < d; j++) mean[j] /= (double)cnt;
+  for (int a = 0; a < d * d; a++) cov[a] = 0.0;
+  for (long i = 0; i < n; i++)
+    if (k[i] == model)
+      for (int a = 0; a < d; a++)
+        for (int b = 0; b < d; b++)
+          cov[a * d + b] += (theta[i * dmax + a] - mean[a]) * (theta[i * dmax + b] - mean[b]);
+  for (int a = 0; a < d * d; a++) cov[a] /= (double)(cnt > 1 ? cnt - 1 : 1);
+  return cnt;
+}

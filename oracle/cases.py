@@ -78,3 +78,39 @@ def fit_pipeline(chk, ht, wl, init, seed: int, nsweep2: int = 1000, Lmax: int = 
 def load_golden(name: str):
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+def sokal_series(seed: int, n: int, stay: float, nmodels: int) -> np.ndarray:
+    """A model-index series with persistence ``stay`` (the kind runStats.xr holds, automix.c:122-124):
+    the chain keeps its model with probability ``stay``, else draws one uniformly."""
+    u = tape(seed, 2 * n)
+    x = np.zeros(n)
+    k = 0
+    for i in range(n):
+        if u[2 * i] > stay:
+            k = int(u[2 * i + 1] * nmodels)
+        x[i] = k
+    return x
+
+
+def ar1_series(seed: int, n: int, phi: float) -> np.ndarray:
+    """A real-valued AR(1) series (sokal() takes doubles; the report writer only feeds it model indices)."""
+    u = tape(seed, 2 * n)
+    z = np.sqrt(-2.0 * np.log(1.0 - u[0::2])) * np.cos(2 * np.pi * u[1::2])
+    x = np.zeros(n)
+    for i in range(1, n):
+        x[i] = phi * x[i - 1] + z[i]
+    return x
+
+
+SOKAL_CASES = [  # (name, kind, seed, n, parameter, nmodels)
+    ("k16", "k", 11, 16, 0.3, 2), ("k64", "k", 12, 64, 0.5, 3), ("k1024", "k", 13, 1024, 0.9, 3),
+    ("k4096", "k", 14, 4096, 0.97, 6), ("k32768", "k", 15, 32768, 0.99, 2), ("k32768b", "k", 16, 32768, 0.2, 6),
+    ("ar256", "ar", 17, 256, 0.8, 0), ("ar8192", "ar", 18, 8192, 0.95, 0), ("ar4", "ar", 19, 4, 0.1, 0),
+    ("const64", "k", 20, 64, 1.0, 2),
+]
+
+
+def sokal_case(c):
+    name, kind, seed, n, par, nm = c
+    return sokal_series(seed, n, par, nm) if kind == "k" else ar1_series(seed, n, par)

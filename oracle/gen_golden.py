@@ -114,5 +114,24 @@ def main():
         print(f, os.path.getsize(os.path.join(cases.GOLDEN_DIR, f)))
 
 
+def sokal_golden():
+    """tests/golden/sokal.npz: the reference's sokal() (user_examples/logwrite.c:354-403, compiled as it lies
+    into oracle/_ref/libref_logwrite.so) on the seeded series of cases.SOKAL_CASES."""
+    assert po.have_ref_logwrite(), "oracle/_ref/libref_logwrite.so is missing: run `make -C oracle ref`"
+    lw = po.RefLogwrite()
+    out = {}
+    for c in cases.SOKAL_CASES:
+        x = cases.sokal_case(c)
+        var, tau, m, rho = lw.sokal(x)
+        out[c[0] + "_vtm"] = np.array([var, tau, float(m)])
+        out[c[0] + "_rho8"] = rho[:8]  # the first autocorrelations the reference left in its input array
+        print(c[0], var, tau, m)
+    np.savez_compressed(os.path.join(cases.GOLDEN_DIR, "sokal.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sokal":
+        sokal_golden()
+    else:
+        main()
+        sokal_golden()

@@ -24,6 +24,7 @@ TARGETS_SO = os.path.join(HERE, "_build", "libamx_hosttargets.so")
 REF_TAPE_SO = os.path.join(HERE, "_ref", "libautomix_tape.so")
 REF_SO = os.path.join(HERE, "_ref", "libautomix.so")
 REF_USERTARGETS_SO = os.path.join(HERE, "_ref", "libref_usertargets.so")
+REF_LOGWRITE_SO = os.path.join(HERE, "_ref", "libref_logwrite.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -116,6 +117,26 @@ class Checker:
         g("rj_sweeps", C.c_int,
           [C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int,
            C.c_int, _dp, _dp, _dp, _ip, _ip, _dp, _ulp, _ip, _dp, _dp, _dp, _ulp, _lp])
+
+        if prefix == "orc":  # posterior summaries: the reference side is RefLogwrite.sokal
+            g("sokal", C.c_int, [C.c_long, _dp, _dp, _dp, _ip])
+            g("model_moments", C.c_long, [C.c_long, C.c_int, _ip, _dp, C.c_int, C.c_int, _dp, _dp])
+
+    def sokal(self, x):
+        """(var, tau, m) of one series, logwrite.c:354-403."""
+        x = f64(x)
+        var, tau, m = C.c_double(), C.c_double(), C.c_int()
+        rc = self._sokal(len(x), _d(x), C.byref(var), C.byref(tau), C.byref(m))
+        if rc != 0:
+            raise ValueError("sokal: length must be a power of two in [4, 2^20]")
+        return var.value, tau.value, m.value
+
+    def model_moments(self, k, theta, model, d):
+        k = i32(k)
+        theta = f64(theta)
+        mean, cov = np.zeros(d), np.zeros((d, d))
+        cnt = self._model_moments(len(k), theta.shape[1], _i(k), _d(theta), model, d, _d(mean), _d(cov))
+        return int(cnt), mean, cov
 
     def _fn(self, name, res, args):
         f = getattr(self.lib, f"{self.prefix}_{name}")
@@ -355,6 +376,25 @@ class RefUserTargets:
         v = np.zeros(d)
         self.lib.ref_cpt_init(k, d, _d(v))
         return v
+
+
+class RefLogwrite:
+    """The reference's report writer compiled as it lies (user_examples/logwrite.c): sokal()."""
+
+    def __init__(self):
+        self.lib = C.CDLL(REF_LOGWRITE_SO)
+        self.lib.sokal.restype = None
+        self.lib.sokal.argtypes = [C.c_int, _dp, _dp, _dp, _ip]
+
+    def sokal(self, x):
+        buf = f64(x).copy()  # the reference overwrites its input with the autocorrelations
+        var, tau, m = C.c_double(), C.c_double(), C.c_int()
+        self.lib.sokal(len(buf), _d(buf), C.byref(var), C.byref(tau), C.byref(m))
+        return var.value, tau.value, m.value, buf
+
+
+def have_ref_logwrite() -> bool:
+    return os.path.exists(REF_LOGWRITE_SO)
 
 
 class RefPristine:

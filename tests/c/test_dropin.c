@@ -161,6 +161,18 @@ static void test_device_plugin(void) {
   CHECK(s->last_error == 0, "GPU stage failed: %s", amx_last_error());
   CHECK(fabs(p0 - 0.3) < 0.01, "posterior model probability");
   CHECK(am.jd.nMixComps[0] >= 1 && am.jd.nMixComps[1] >= 2, "mixture fit");
+  /* posterior summaries: Sokal's tau of chain 0's model-index series (what the reference's report writer prints)
+   * and per-model moments over the population.  toy1 model 1: 0.2 N(-3, 2^2) + 0.8 N(2, 1): mean 1, var 5.6 */
+  unsigned long long c0 = 0, c1 = 0;
+  double pm[2], pc[4], plp;
+  CHECK(am.st.nkeep == 512 && am.st.m >= 2 && am.st.tau > 0.5 && am.st.tau < 200.0 && am.st.var > 0.0 && am.st.var < 0.3,
+        "Sokal summary: nkeep %d var %g tau %g m %d", am.st.nkeep, am.st.var, am.st.tau, am.st.m);
+  CHECK(amx_sampler_posterior(&am, 0, &c0, pm, pc, &plp) == 0, "posterior moments: %s", amx_last_error());
+  printf("  tau = %.2f (m = %d); model 1 over %llu chains: mean %.3f (true 1.0) var %.3f (true 5.6)\n", am.st.tau, am.st.m, c0,
+         pm[0], pc[0]);
+  CHECK(fabs(pm[0] - 1.0) < 0.12 && fabs(pc[0] - 5.6) < 0.4, "model-1 posterior mean and variance");
+  CHECK(amx_sampler_posterior(&am, 1, &c1, pm, pc, NULL) == 0 && c0 + c1 == 32768ull, "one draw per chain (%llu + %llu)", c0, c1);
+  CHECK(pc[1] == pc[2], "covariance is symmetric");
   /* the fitted proposal on disk, and a second sampler that starts from it: stages 1-2 are skipped */
   CHECK(amx_sampler_save_proposal(&am, "/tmp/amx_toy1_mix.data") == 0, "save proposal");
   amSampler am2;

@@ -94,3 +94,32 @@ def test_tape_overrun_is_reported(orc, ht):
     mix = {k[4:]: g[k] for k in g if k.startswith("mix_")}
     orc.rj_sweeps(mix, ptr, s0, 50)
     assert orc.tape_overrun()
+
+
+def test_sokal_oracle_against_reference_golden(orc):
+    """orc_sokal (own radix-2 transform) against the reference's sokal() outputs (logwrite.c:354-403)."""
+    g = cases.load_golden("sokal")
+    for c in cases.SOKAL_CASES:
+        x = cases.sokal_case(c)
+        var, tau, m = orc.sokal(x)
+        gv, gt, gm = g[c[0] + "_vtm"]
+        assert m == int(gm), c[0]
+        assert abs(var - gv) <= 1e-12 * max(1.0, abs(gv)), c[0]
+        if np.isnan(gt):
+            assert np.isnan(tau)
+        else:
+            assert abs(tau - gt) <= 1e-10 * max(1.0, abs(gt)), (c[0], tau, gt)
+    with pytest.raises(ValueError):
+        orc.sokal(np.zeros(100))
+
+
+def test_model_moments_oracle(orc):
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 3, 500).astype(np.int32)
+    th = rng.normal(size=(500, 4)) * [1, 2, 3, 4] + [10, -5, 0, 1]
+    for mdl, d in ((0, 2), (1, 4), (2, 1)):
+        cnt, mean, cov = orc.model_moments(k, th, mdl, d)
+        sel = th[k == mdl][:, :d]
+        assert cnt == len(sel)
+        assert np.allclose(mean, sel.mean(0), rtol=1e-13, atol=1e-13)
+        assert np.allclose(cov, np.cov(sel.T).reshape(d, d), rtol=1e-12, atol=1e-13)

@@ -107,3 +107,18 @@ def test_em_iteration_by_iteration(orc, ref):
         b = ref.fit_mixture(g["x"], Lmax=12, maxit=maxit)
         for key in ("lam", "mu", "B", "trace_L", "trace_loglik", "trace_cost", "trace_ann"):
             assert np.array_equal(a[key], b[key]), (maxit, key)
+
+
+def test_sokal_oracle_vs_reference(po, orc):
+    """Fresh series (not the committed ones) through the reference's sokal() compiled as it lies."""
+    if not po.have_ref_logwrite():
+        pytest.skip("oracle/_ref/libref_logwrite.so not built")
+    lw = po.RefLogwrite()
+    for i, (n, stay) in enumerate([(8, 0.5), (128, 0.0), (512, 0.8), (2048, 0.95), (16384, 0.98), (65536, 0.9)]):
+        x = cases.sokal_series(500 + i, n, stay, 4)
+        rv, rt, rm, rho = lw.sokal(x)
+        ov, ot, om = orc.sokal(x)
+        assert om == rm, (n, om, rm)
+        assert abs(ov - rv) <= 1e-12 * max(1.0, abs(rv))
+        assert abs(ot - rt) <= 1e-10 * max(1.0, abs(rt)), (n, ot, rt)
+        assert abs(rho[0] - 1.0) < 1e-12
