@@ -3,6 +3,7 @@
  * reader's (logwrite.c:27-109).  No GPU is touched: initAMSampler and the file routines are host C. */
 #include "automix.h"
 
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -79,6 +80,47 @@ int main(int argc, char **argv) {
   fprintf(f, "3\n1\n3\n2\n1.0\n2\n0.5\n0\n1\n0.4\n0\n1\n");
   fclose(f);
   CHECK(amx_sampler_load_proposal(&c, path2) != 0, "weights that do not sum to one are rejected");
+  /* Either side reads the other's files: the reference's own reader and writer (user_examples/logwrite.c,
+   * compiled as it lies into oracle/_ref/libref_logwrite.so; its structs have this header's layout). */
+  if (argc > 2) {
+    void *h = dlopen(argv[2], RTLD_NOW | RTLD_LOCAL);
+    CHECK(h != NULL, "dlopen libref_logwrite.so");
+    if (h) {
+      int (*ref_read)(char *, amSampler *) = (int (*)(char *, amSampler *))dlsym(h, "read_mixture_params");
+      void (*ref_write)(char *, proposalDist) = (void (*)(char *, proposalDist))dlsym(h, "write_mix_to_file");
+      CHECK(ref_read && ref_write, "reference reader / writer symbols");
+      char stem[512], stem2[512], file2[560];
+      snprintf(stem, sizeof(stem), "%s/prop", dir); /* the reference appends _mix.data */
+      snprintf(stem2, sizeof(stem2), "%s/byref", dir);
+      snprintf(file2, sizeof(file2), "%s_mix.data", stem2);
+      amSampler r, w;
+      initAMSampler(&r, 3, dims, lp, NULL);
+      initAMSampler(&w, 3, dims, lp, NULL);
+      CHECK(ref_read(stem, &r) == EXIT_SUCCESS, "the reference's reader accepts our file");
+      ref_write(stem2, a.jd);
+      CHECK(amx_sampler_load_proposal(&w, file2) == 0, "our loader accepts the reference writer's file");
+      for (int k = 0; k < 3; k++) {
+        const int d = dims[k], L = a.jd.nMixComps[k];
+        CHECK(r.jd.nMixComps[k] == L && w.jd.nMixComps[k] == L, "component counts across implementations");
+        for (int l = 0; l < L; l++) {
+          CHECK(r.jd.lambda[k][l] == b.jd.lambda[k][l], "weights: their reader == our reader, bit for bit");
+          CHECK(fabs(w.jd.lambda[k][l] - a.jd.lambda[k][l]) < 2e-6, "weights through their six-decimal writer");
+          for (int i = 0; i < d; i++) {
+            CHECK(r.jd.mu[k][l][i] == a.jd.mu[k][l][i], "means through their reader are bit-identical");
+            CHECK(fabs(w.jd.mu[k][l][i] - a.jd.mu[k][l][i]) < 5.1e-7, "means through their writer");
+            for (int j = 0; j <= i; j++) {
+              CHECK(r.jd.B[k][l][i][j] == a.jd.B[k][l][i][j], "factors through their reader are bit-identical");
+              CHECK(fabs(w.jd.B[k][l][i][j] - a.jd.B[k][l][i][j]) < 5.1e-7, "factors through their writer");
+            }
+          }
+        }
+        for (int i = 0; i < d; i++) CHECK(r.jd.sig[k][i] == a.jd.sig[k][i], "scales through their reader");
+      }
+      freeAMSampler(&r);
+      freeAMSampler(&w);
+      printf("cross-read with the reference's logwrite.c: done\n");
+    }
+  }
   freeAMSampler(&a);
   freeAMSampler(&b);
   freeAMSampler(&c);

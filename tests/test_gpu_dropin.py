@@ -48,7 +48,15 @@ def test_proposal_file_round_trip(tmp_path):
     exe = os.path.join(ROOT, "tests", "c", "test_proposal_io")
     lib = os.path.join(ROOT, "automix_b200", "lib")
     subprocess.run([os.environ.get("CC", "gcc"), "-O2", "-Wall", os.path.join(ROOT, "tests", "c", "test_proposal_io.c"),
-                    "-I", os.path.join(ROOT, "include"), "-L", lib, "-lautomix", "-lm", "-Wl,-rpath," + lib, "-o", exe],
+                    "-I", os.path.join(ROOT, "include"), "-L", lib, "-lautomix", "-lm", "-ldl", "-Wl,-rpath," + lib, "-o", exe],
                    check=True)
-    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    args = [exe, str(tmp_path)]
+    ref_lw = os.path.join(ROOT, "oracle", "_ref", "libref_logwrite.so")
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True)
+    if os.path.exists(ref_lw):  # cross-read with the reference's own reader and writer
+        args.append(ref_lw)
+    r = subprocess.run(args, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+    if os.path.exists(ref_lw):
+        assert "cross-read" in r.stdout
