@@ -81,10 +81,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 // ---- counter-based per-chain RNG: Philox4x32-10 ---------------------------------------
-// key = 64-bit seed, counter = (block index of this chain's stream, chain id).  One block
-// yields two 53-bit uniforms in (0,1): u = (x>>11 + 0.5) * 2^-53, never 0 or 1 (the
-// reference's generator can return exactly 0, which sends log(0) into Box-Muller;
-// SURVEY.md A.4).
+// key = 64-bit seed, counter = (block index of this chain's stream, chain id).  One block yields four
+// uniforms u = (w + 0.5) * 2^-32 in (0,1), one per 32-bit word: the resolution of the reference's own
+// generator (sdrand returns a 31-bit integer times 2^-31, automix.c:1300-1305), but never 0 or 1 (the
+// reference's can return exactly 0, which sends log(0) into Box-Muller).
 __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -100,20 +100,22 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
   }
 }
 
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-  const unsigned long long x = ((unsigned long long)hi << 32) | lo;
-  return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+// (w + 0.5) * 2^-32 without an integer-to-double conversion: the word becomes the top of the mantissa of a
+// double in [1, 2), and subtracting 1 - 2^-33 is exact.
+__device__ __forceinline__ double u32_to_unit(uint32_t w) {
+  return __hiloint2double((int)(0x3ff00000u | (w >> 12)), (int)(w << 20)) - (1.0 - 1.0 / 8589934592.0);
 }
 
 struct PhiloxStream {
   uint32_t k0, k1, id0, id1;
   unsigned long long n;  // uniforms consumed so far by this chain
-  double spare;
-  __device__ __forceinline__ void block(unsigned long long b, double &u0, double &u1) const {
-    uint32_t c[4] = {(uint32_t)b, (uint32_t)(b >> 32), id0, id1};
+  uint32_t w1, w2, w3;   // words of the current block not handed out yet, next first
+  __device__ __forceinline__ void block(unsigned long long b, uint32_t (&c)[4]) const {
+    c[0] = (uint32_t)b;
+    c[1] = (uint32_t)(b >> 32);
+    c[2] = id0;
+    c[3] = id1;
     philox4x32_10(c, k0, k1);
-    u0 = u53(c[0], c[1]);
-    u1 = u53(c[2], c[3]);
   }
   __device__ __forceinline__ void open(unsigned long long seed, unsigned long long chain,
                                        unsigned long long consumed) {
@@ -122,21 +124,32 @@ struct PhiloxStream {
     id0 = (uint32_t)chain;
     id1 = (uint32_t)(chain >> 32);
     n = consumed;
-    spare = 0.0;
-    if (n & 1ull) {
-      double a;
-      block(n >> 1, a, spare);
+    w1 = w2 = w3 = 0u;
+    const int r = (int)(n & 3ull);
+    if (r) {  // resume in the middle of a block
+      uint32_t c[4];
+      block(n >> 2, c);
+      w1 = r == 1 ? c[1] : (r == 2 ? c[2] : c[3]);
+      w2 = r == 1 ? c[2] : c[3];
+      w3 = c[3];
     }
   }
   __device__ __forceinline__ double next() {
-    double r;
-    if ((n & 1ull) == 0) {
-      block(n >> 1, r, spare);
+    uint32_t w;
+    if ((n & 3ull) == 0) {
+      uint32_t c[4];
+      block(n >> 2, c);
+      w = c[0];
+      w1 = c[1];
+      w2 = c[2];
+      w3 = c[3];
     } else {
-      r = spare;
+      w = w1;
+      w1 = w2;
+      w2 = w3;
     }
     n++;
-    return r;
+    return u32_to_unit(w);
   }
   __device__ __forceinline__ bool overrun() const { return false; }
 };

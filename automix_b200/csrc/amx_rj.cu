@@ -20,8 +20,6 @@
 
 namespace amx {
 
-constexpr int kRjThreads = 128;
-constexpr int kRjWarps = kRjThreads / 32;
 
 __global__ void rj_gamma_kernel(double *g, unsigned long long sweep0, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,6 +108,7 @@ __device__ __noinline__
 }
 
 // ---- the fused sweep kernel ------------------------------------------------------------------
+enum { kPhaseBlock = 0, kPhaseCoord, kPhaseJump, kPhaseIdle };
 template <class CFG, class TGT, class RNG>
 __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCKS : 1)) rj_sweep_kernel(RjLaunch a, int staged) {
   extern __shared__ double smem[];
@@ -117,6 +116,10 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   __shared__ int s_clp[AMX_MAX_MODELS];
   __shared__ unsigned long long s_cnt[8];
   __shared__ int s_status;
+  // allocation weights of the jump: [component][thread] in shared memory for the register-resident configurations
+  __shared__ double s_pa[(CFG::DMAX <= 8) ? CFG::LMAX * kRjThreads : 1];
+  AllocVec<CFG> pa;
+  if constexpr (CFG::DMAX <= 8) pa.p = s_pa + threadIdx.x;
 
   const void *pb, *tb;
   stage_blobs(a, smem, staged != 0, pb, tb);
@@ -154,23 +157,53 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   for (int s = 0; s < a.nsweeps; s++) {
     const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
     const int d = P.h->dims[c.k];
-    if (sweep_i % 10ull == 0ull) {  // block move every 10th sweep (:95, :148)
-      rwm_block_propose(c, P, u, md);
-      const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
-      rwm_block_finish(c, P, u, lpn);
-      c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
-    } else {
-      sync_proposal(c, d);
-      for (int j = 0; j < d; j++) {
-        rwm_coord_propose(c, P, u, j, md);
-        const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
-        rwm_coord_finish(c, u, j, lpn);
+    // A sweep is a sequence of phases -- propose | evaluate the log-posterior | accept -- and the loop below holds
+    // ONE copy of the plug-in evaluation and of each proposal kind (three inlined copies made the kernel 130 KB of
+    // SASS and instruction fetch its second largest stall).  Every 10th sweep is a block move (:95, :148), uniform
+    // over the grid; otherwise coordinate phase j runs on the lanes whose model has more than j coordinates and the
+    // jump waits for the widest model in the warp, so the lanes of a warp always take it together.
+    const bool blockmove = (sweep_i % 10ull == 0ull);
+    if constexpr (CFG::DMAX <= 8) {
+      int last = 1;
+      if (blockmove) {
+        c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
+      } else {
+        sync_proposal(c, d);
+        last = __reduce_max_sync(0xffffffffu, d);
+        c.flops += (unsigned)(d * (s_clp[c.k] + 12));
       }
-      c.flops += (unsigned)(d * (s_clp[c.k] + 12));
+      for (int ph = 0; ph <= last; ph++) {
+        const int kind = (ph == last) ? kPhaseJump : (blockmove ? kPhaseBlock : (ph < d ? kPhaseCoord : kPhaseIdle));
+        if (kind == kPhaseBlock) rwm_block_propose(c, P, u, md);
+        else if (kind == kPhaseCoord) rwm_coord_propose(c, P, u, ph, md);
+        else if (kind == kPhaseJump) rj_propose(c, P, u, a.gam[s], md, s_clp, pa);
+        double lpn = 0.0;
+        if (kind != kPhaseIdle) lpn = eval_target<CFG, TGT>(T, kind == kPhaseJump ? c.kn : c.k, c.thn);
+        if (kind == kPhaseBlock) rwm_block_finish(c, P, u, lpn);
+        else if (kind == kPhaseCoord) rwm_coord_finish(c, u, ph, lpn);
+        else if (kind == kPhaseJump) rj_finish(c, P, u, lpn, a.adapt != 0);
+      }
+    } else {
+      // large configurations (vectors in local memory, one or two CTAs per SM): code size is not what limits them,
+      // and the straight-line form measured 5 % faster
+      if (blockmove) {
+        rwm_block_propose(c, P, u, md);
+        const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
+        rwm_block_finish(c, P, u, lpn);
+        c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
+      } else {
+        sync_proposal(c, d);
+        for (int j = 0; j < d; j++) {
+          rwm_coord_propose(c, P, u, j, md);
+          const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
+          rwm_coord_finish(c, u, j, lpn);
+        }
+        c.flops += (unsigned)(d * (s_clp[c.k] + 12));
+      }
+      rj_propose(c, P, u, a.gam[s], md, s_clp, pa);
+      const double lpn = eval_target<CFG, TGT>(T, c.kn, c.thn);
+      rj_finish(c, P, u, lpn, a.adapt != 0);
     }
-    rj_propose(c, P, u, a.gam[s], md, s_clp);
-    const double lpn = eval_target<CFG, TGT>(T, c.kn, c.thn);
-    rj_finish(c, P, u, lpn, a.adapt != 0);
     if (c.lp != c.lp) status |= 2;
 
     // model-visit histogram: one ballot per model, lane 0 adds the population count
@@ -189,6 +222,10 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
     }
   }
   if (u.overrun()) status |= 1;
+  // every chain tries one jump per sweep and one block move per 10th sweep: grid-uniform counts, set here so
+  // that the per-sweep increments inside the phase functions (needed by the split kernels) are dead code
+  c.try_j = (unsigned)a.nsweeps;
+  c.try_b = (unsigned)((a.sweep0 + (unsigned long long)a.nsweeps + 9ull) / 10ull - (a.sweep0 + 9ull) / 10ull);
 
   if (active) {
     store_chain(c, a.st, id);
@@ -236,6 +273,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
   __shared__ int s_clp[AMX_MAX_MODELS];
   __shared__ unsigned s_hist[kRjWarps][CFG::NMAX];
   __shared__ unsigned long long s_cnt[8];
+  AllocVec<CFG> pa;
   ProposalView P;
   P.bind(a.prop_blob);
   const int nm = P.h->nmodels;
@@ -282,7 +320,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
       if (j < d) rwm_coord_finish(c, u, j, lpn);
       break;
     case kPhJumpPropose:
-      rj_propose(c, P, u, a.gam[s], a.modes, s_clp);
+      rj_propose(c, P, u, a.gam[s], a.modes, s_clp, pa);
       keval = c.kn;
       break;
     case kPhJumpFinish:
@@ -484,8 +522,13 @@ static int launch_sweeps(const RjLaunch &a) {
     const unsigned per_sm = e ? (unsigned)atoi(e) : (CFG::DMAX <= 20 ? 2u : 1u);
     const unsigned cap = (unsigned)sms * (per_sm ? per_sm : 1u);
     if (grid > cap) grid = cap;
-    AMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  staged ? (int)((smem * per_sm * 100) / (228 * 1024) + 5) : 0));
+    // shared memory per SM: per resident CTA the staged blobs, the static arrays (allocation weights, histograms)
+    // and the driver's 1 KB; whatever is left stays L1 for the chains' local vectors
+    cudaFuncAttributes fa;
+    AMX_CUDA(cudaFuncGetAttributes(&fa, kern));
+    const size_t per_cta = smem + fa.sharedSizeBytes + 1024;
+    int pct = (int)((per_cta * per_sm * 100) / (228 * 1024) + 3);
+    AMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct));
   }
   kern<<<grid, kRjThreads, smem, stream()>>>(a, staged);
   count_launch();

@@ -7,6 +7,8 @@
 //   * the split kernels used with a host callback (propose -> host evaluates -> finish).
 #pragma once
 
+#include <type_traits>
+
 #include "amx_common.cuh"
 #include "amx_targets.cuh"
 
@@ -22,6 +24,26 @@ using RjCfgL = RjCfg<20, 8, 16>;   // large: coal-mining (d<=13), the scaling wo
 using RjCfgG = RjCfg<AMX_MAX_DIM, AMX_MAX_COMPS, AMX_MAX_MODELS>;  // general (local memory)
 
 constexpr double kHalfLog2Pi = 0.9189385332046727;  // literal at automix.c:1052
+constexpr int kRjThreads = 128;
+constexpr int kRjWarps = kRjThreads / 32;
+
+// A per-thread scratch vector kept in shared memory, laid out [element][thread] (conflict-free): a run-time
+// index costs one LDS/STS, where a register array needs a select chain per access and a local array an L1 trip.
+struct LaneVec {
+  double *p;
+  __device__ __forceinline__ double get(int i) const { return p[i * kRjThreads]; }
+  __device__ __forceinline__ void set(int i, double v) { p[i * kRjThreads] = v; }
+};
+// The large configurations keep the same vector in local memory: their shared memory holds the staged blobs and
+// what is left of the SM's 228 KB must stay L1 for the chains' vectors (measured: every KB of carve-out costs).
+template <int N>
+struct LocalVec {
+  double v[N];
+  __device__ __forceinline__ double get(int i) const { return v[i]; }
+  __device__ __forceinline__ void set(int i, double x) { v[i] = x; }
+};
+template <class CFG>
+using AllocVec = typename std::conditional<(CFG::DMAX <= 8), LaneVec, LocalVec<CFG::LMAX>>::type;
 
 // optional modes (amSampler.student_T_dof, amSampler.doPerm)
 // compile-time "no optional modes": the branches below fold away (the small configuration uses this)
@@ -124,33 +146,29 @@ __device__ __forceinline__ void rwm_coord_finish(ChainRegs<CFG> &c, U &u, int j,
   }
 }
 
-// allocation probabilities of point x under model k's mixture (:1094-1110 / :1217-1232)
-template <class CFG>
-__device__ __forceinline__ void alloc_probs(const ProposalView &P, int k, const double (&x)[CFG::DMAX],
-                                            double (&p)[CFG::LMAX]) {
+// Unnormalised allocation weights lambda_l N(x; mu_l, B_l B_l^T) of point x under model k's mixture and their
+// sum (:1094-1108 / :1217-1230).  The callers divide only where the reference's quotient is consumed: the
+// forward allocation scans all of palloc (:1111-1123), the reverse one reads palloc[ln] alone (:1234).
+template <class CFG, class PA>
+__device__ __forceinline__ double alloc_weights(const ProposalView &P, int k, const double (&x)[CFG::DMAX], PA &p) {
   const int d = P.h->dims[k], L = P.h->ncomp[k];
   double r[CFG::DMAX];
   double s = 0.0;
   for (int l = 0; l < L; l++) {
     const double *rec = P.rec(k, l);
     const double v = exp(rec[1] + (fma(-0.5, solve_lower<CFG::DMAX>(rec, d, x, r), rec[3])));
-    aset(p, l, v);
+    p.set(l, v);
     s += v;
   }
-  if (s > 0) {
-    for (int l = 0; l < L; l++) aset(p, l, aget(p, l) / s);
-  } else {
-    for (int l = 0; l < L; l++) aset(p, l, 1.0 / L);
-  }
+  return s;
 }
 
 // ---- between-model move, everything up to the log-posterior of the proposal -------------
-template <class CFG, class U, class MD>
+template <class CFG, class U, class MD, class PA>
 __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView &P, U &u, double gam,
-                                           const MD &md, const int *clp_tab) {
+                                           const MD &md, const int *clp_tab, PA &pa) {
   const int nm = P.h->nmodels;
   const int k = c.k, d = P.h->dims[k], L = P.h->ncomp[k];
-  double pa[CFG::LMAX];
   double wk[CFG::DMAX];
   c.try_j++;
 
@@ -158,18 +176,22 @@ __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView
   int l = 0;
   double log_pa = 0.0;
   if (L > 1) {
-    alloc_probs<CFG>(P, k, c.th, pa);
+    const double sw = alloc_weights<CFG>(P, k, c.th, pa);
     const double uu = u.next();
-    double t = 0.0;
+    const double flat = 1.0 / L;  // the reference's fallback when every weight underflows (:1107-1110)
+    double t = 0.0, pl = 0.0;
     bool found = false;
     for (int i = 0; i < L; i++) {
-      t += aget(pa, i);
+      const double pi = (sw > 0) ? pa.get(i) / sw : flat;
+      if (i == 0) pl = pi;  // component 0 if the scan never fires
+      t += pi;
       if (!found && uu < t) {
         l = i;
+        pl = pi;
         found = true;
       }
     }
-    log_pa = log(aget(pa, l));
+    log_pa = log(pl);
     c.flops += (unsigned)(L * (d * d + 3 * d + 6));
   }
   // 9.2 standardise through component l (:1127-1135)
@@ -278,8 +300,8 @@ __device__ __forceinline__ void rj_propose(ChainRegs<CFG> &c, const ProposalView
   // 9.5 reverse allocation (:1216-1235)
   double log_pan = 0.0;
   if (Ln > 1) {
-    alloc_probs<CFG>(P, kn, c.thn, pa);
-    log_pan = log(aget(pa, ln));
+    const double sw = alloc_weights<CFG>(P, kn, c.thn, pa);
+    log_pan = log((sw > 0) ? pa.get(ln) / sw : 1.0 / Ln);
     c.flops += (unsigned)(Ln * (dn * dn + 3 * dn + 6));
   }
   c.kn = kn;
