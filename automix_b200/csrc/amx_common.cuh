@@ -151,6 +151,13 @@ struct PhiloxStream {
     n++;
     return u32_to_unit(w);
   }
+  // random access: uniform number i of this chain's stream (what the i-th next() returns)
+  __device__ __forceinline__ double at(unsigned long long i) const {
+    uint32_t c[4];
+    block(i >> 2, c);
+    const int r = (int)(i & 3ull);
+    return u32_to_unit(r == 0 ? c[0] : (r == 1 ? c[1] : (r == 2 ? c[2] : c[3])));
+  }
   __device__ __forceinline__ bool overrun() const { return false; }
 };
 
@@ -173,6 +180,11 @@ struct TapeStream {
     else over = true;
     n++;
     return r;
+  }
+  __device__ __forceinline__ double at(unsigned long long i) {
+    if (i < len) return p[i];
+    over = true;
+    return 0.5;
   }
   __device__ __forceinline__ bool overrun() const { return over; }
 };

@@ -7,6 +7,7 @@
 // so chain 0 fed an injected tape IS the reference chain, step for step.  The chains differ only
 // in their counter-based RNG stream; a whole population advances in the wall time of one chain,
 // which is what stage 2 needs when it pools the stored samples of many chains.
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -160,6 +161,219 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_adapt_kernel(RwmArgs a) {
 }
 
 
+// ---- speculative form: one WARP per chain, exact semantics ------------------------------------------
+// A single chain is a sequence of accept/reject decisions, each needing one log-posterior evaluation of a
+// proposal that depends on the decisions before it -- on a GPU a thread walking that sequence is bound by the
+// latency of one evaluation after another (coal-mining, d = 13: 12.5 s for the reference's schedule).  But the
+// uniforms a step consumes do not depend on the decisions (with Gaussian proposals every coordinate step takes
+// exactly three), so the proposal noise of the next steps is known in advance and the only unknown is the
+// accept/reject path.  The warp therefore evaluates the whole decision tree of the next five coordinate steps
+// at once: lane (2^t - 1) + p owns the node at depth t reached by the accept pattern p of the steps before it,
+// replays that prefix without evaluating anything (the proposals and the adapted scales along it are cheap),
+// and evaluates the log-posterior of its own proposal.  Every node then knows the log-posterior of its current
+// state (its last accepted ancestor's, by shuffle) and decides; five shuffles walk the true path, and every lane
+// commits it.  31 evaluations run in the time of one and five steps retire per round, with the arithmetic of
+// the sequential kernel operation for operation, so the chain is the same chain bit for bit (the tests run both
+// on the same injected tape).  Block-move sweeps (a tenth of the sweeps after burn-in) are taken one at a time.
+constexpr int kSpecDepth = 5;
+
+template <int DMAX, class TGT, class RNG>
+__global__ void __launch_bounds__(32) rwm_spec_kernel(RwmArgs a) {
+  TGT T;
+  T.bind(a.tgt_blob, a.tgt_flags);
+  const long id = blockIdx.x;
+  const int lane = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int d = a.d, k = a.model_k;
+  RNG u;
+  if constexpr (std::is_same<RNG, TapeStream>::value) u.open(a.tape, a.tape_stride, (unsigned long long)id, 0ull);
+  else u.open(a.seed, (unsigned long long)id, 0ull);
+
+  double cur[DMAX], sig[DMAX];
+  double xc[DMAX], sg[DMAX];  // this lane's speculative copy of the state and the scales (one scratch for every use)
+  int nacc[DMAX], ntry[DMAX];
+#pragma unroll
+  for (int i = 0; i < DMAX; i++) {
+    cur[i] = xc[i] = (i < d) ? a.init[i] : 0.0;
+    sig[i] = sg[i] = 10.0;  // :595
+    nacc[i] = ntry[i] = 0;
+  }
+  double lp = T.template eval<DMAX>(k, xc);
+  const long nstore = 1000L * d;
+  double *out = a.samples_out + (size_t)id * nstore * d;
+  long stored = 0;
+  int ntrace = 0;
+  const double alphastar = 0.25;
+  int status = 0;
+
+  // the node of the decision tree this lane evaluates: depth and the accept pattern of the steps above it
+  const int t_me = 31 - __clz(lane + 1);
+  const int p_me = lane + 1 - (1 << t_me);
+
+  auto end_of_sweep = [&](int sweep) {  // :642-655
+    const int remain = a.nsweepr - sweep;
+    if (remain < 10000 * d && remain % 10 == 0) {
+      if (stored < nstore && lane == 0)
+        for (int q = 0; q < d; q++) out[stored * d + q] = cur[q];
+      stored++;
+    }
+    if (sweep % 100 == 0) {
+      if (id == 0 && lane == 0 && a.sig_trace0 != nullptr)
+        for (int q = 0; q < d; q++) {
+          a.sig_trace0[(size_t)ntrace * d + q] = sig[q];
+          a.acc_trace0[(size_t)ntrace * d + q] = (double)nacc[q] / (double)ntry[q];
+        }
+      ntrace++;
+    }
+  };
+
+  unsigned long long n = 0;  // index of the next uniform of the chain's stream
+  int sweep = 1, j = 0;      // next step: coordinate j of `sweep`; j == 0 <=> the sweep's first uniform is not drawn yet
+  while (sweep <= a.nsweepr) {
+    if (j == 0) {
+      const double uu = u.at(n);
+      n++;
+      if (sweep > a.nburn && uu < 0.1) {  // block move (:606-617): every lane does the same work
+        const int npairs = d >> 1;
+        double za = 0.0, zb = 0.0;
+        if (lane < npairs) {  // gauss_pair
+          const double ua = u.at(n + 2 * lane), ub = u.at(n + 2 * lane + 1);
+          const double r = sqrt(-2.0 * log(ua));
+          double sn, cs;
+          sincos(6.283185307179586476925 * ub, &sn, &cs);
+          za = r * sn;
+          zb = r * cs;
+        } else if (lane == npairs && (d & 1)) {  // gauss_single
+          const double ua = u.at(n + 2 * lane), ub = u.at(n + 2 * lane + 1);
+          za = sqrt(-2.0 * log(ua)) * sin(6.283185307179586476925 * ub);
+        }
+#pragma unroll
+        for (int i = 0; i < DMAX; i++) xc[i] = cur[i];
+        for (int i = 0; i < d; i++) {
+          const double z = __shfl_sync(full, (i & 1) ? zb : za, i >> 1);
+          xc[i] = fma(sig[i], z, cur[i]);
+        }
+        n += 2ull * (unsigned long long)((d + 1) >> 1);
+        const double lpn = T.template eval<DMAX>(k, xc);
+        const double uacc = u.at(n);
+        n++;
+        if (uacc < mh_prob(lpn - lp)) {
+#pragma unroll
+          for (int i = 0; i < DMAX; i++) cur[i] = xc[i];
+          lp = lpn;
+        }
+        end_of_sweep(sweep);
+        sweep++;
+        continue;
+      }
+    }
+    // how many coordinate steps the window holds: it may run into the following sweeps, and stops in front of a
+    // block-move sweep (whose first uniform is then read again at the top) and at the end of the schedule
+    int m = 0;
+    {
+      int s2 = sweep, j2 = j;
+      unsigned long long n2 = n;
+      while (m < kSpecDepth) {
+        if (j2 == 0 && m > 0) {
+          if (s2 > a.nsweepr) break;
+          const double uu2 = u.at(n2);
+          if (s2 > a.nburn && uu2 < 0.1) break;
+          n2++;
+        }
+        n2 += 3;
+        m++;
+        if (++j2 == d) {
+          j2 = 0;
+          s2++;
+        }
+      }
+    }
+    // step t of the window: coordinate, sweep and position in the uniform stream
+    auto coord_of = [&](int t) { return (j + t) % d; };
+    auto sweep_of = [&](int t) { return sweep + (j + t) / d; };
+    auto first_uniform_of = [&](int t) { return n + 3ull * (unsigned long long)t + (unsigned long long)((j + t) / d); };
+
+    // proposal noise of the window: lane t draws step t's variate (gauss(), :1639-1661), everyone gets all of them
+    double zmine = 0.0;
+    if (lane < m) {
+      const unsigned long long nt = first_uniform_of(lane);
+      const double ua = u.at(nt), ub = u.at(nt + 1);
+      zmine = sqrt(-2.0 * log(ua)) * sin(6.283185307179586476925 * ub);
+    }
+    double z[kSpecDepth];
+#pragma unroll
+    for (int t = 0; t < kSpecDepth; t++) z[t] = __shfl_sync(full, zmine, t);
+
+    // replay the prefix of this lane's node, then evaluate its proposal
+    const bool node = t_me < m;
+    double lpn = 0.0;
+    if (node) {
+#pragma unroll
+      for (int i = 0; i < DMAX; i++) {
+        xc[i] = cur[i];
+        sg[i] = sig[i];
+      }
+      for (int q = 0; q < t_me; q++) {
+        const int c = coord_of(q);
+        const double si = aget(sg, c), gam = a.gtab[sweep_of(q) - 1];
+        if ((p_me >> q) & 1) {
+          aset(xc, c, fma(si, aget(z, q), aget(xc, c)));
+          aset(sg, c, max_m(0.0, si - gam * (alphastar - 1.0)));
+        } else {
+          aset(sg, c, max_m(0.0, si - gam * alphastar));
+        }
+      }
+      const int c = coord_of(t_me);
+      aset(xc, c, fma(aget(sg, c), aget(z, t_me), aget(xc, c)));
+      lpn = T.template eval<DMAX>(k, xc);
+    }
+    // the log-posterior of the node's current state: its last accepted ancestor's proposal, else the chain's
+    int src = lane;
+    if (p_me != 0) {
+      const int jh = 31 - __clz(p_me);
+      src = (1 << jh) - 1 + (p_me & ((1 << jh) - 1));
+    }
+    const double lpa = __shfl_sync(full, lpn, src);
+    const double lpc = (p_me != 0) ? lpa : lp;
+    int dec = 0;
+    if (node) {
+      const double uacc = u.at(first_uniform_of(t_me) + 2);
+      const double acc = min_m(1.0, mh_prob(lpn - lpc));  // :627
+      dec = (uacc < acc) ? 1 : 0;
+    }
+    // walk the true path
+    int path = 0;
+    for (int t = 0; t < m; t++) path |= __shfl_sync(full, dec, (1 << t) - 1 + path) << t;
+    // commit it: every lane applies the same m steps (:628-640)
+    for (int t = 0; t < m; t++) {
+      const int c = coord_of(t), sw = sweep_of(t);
+      const double si = aget(sig, c), gam = a.gtab[sw - 1];
+      const double lpt = __shfl_sync(full, lpn, (1 << t) - 1 + (path & ((1 << t) - 1)));
+      if ((path >> t) & 1) {
+        nacc[c]++;
+        ntry[c]++;
+        aset(cur, c, fma(si, aget(z, t), aget(cur, c)));
+        lp = lpt;
+        aset(sig, c, max_m(0.0, si - gam * (alphastar - 1.0)));
+      } else {
+        ntry[c]++;
+        aset(sig, c, max_m(0.0, si - gam * alphastar));
+      }
+      if (c == d - 1) end_of_sweep(sw);
+    }
+    const int q = j + m;
+    n += 3ull * (unsigned long long)m + (unsigned long long)((j + m - 1) / d);
+    sweep += q / d;
+    j = q % d;
+  }
+  if (lane == 0)
+    for (int q = 0; q < d; q++) a.sig_out[(size_t)id * d + q] = sig[q];
+  if (u.overrun()) status |= 1;
+  if (lp != lp) status |= 2;
+  if (status) atomicOr(a.status, status);
+}
+
+
 // ---- split form for HOST log-posterior callbacks ---------------------------------------------------
 // Same chain, cut at every log-posterior evaluation: kernel j of a sweep finishes proposal j-1 with
 // the value the host returned and makes proposal j.  State lives in global memory between kernels.
@@ -285,8 +499,30 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_split_kernel(RwmArgs a, RwmSp
   if (status) atomicOr(a.status, status);
 }
 
+// Few chains: latency is what matters, give each chain a warp (speculative kernel).  Many chains (pooled
+// stage-1 populations): throughput matters, one thread per chain.  Student-t proposals draw a data-dependent
+// number of uniforms per step (rgamma's rejection loop), which the look-ahead cannot index: sequential kernel.
+static bool rwm_use_spec(const RwmArgs &a) {
+  const char *e = getenv("AMX_RWM_SPEC");
+  if (e) return atoi(e) != 0 && a.dof == 0;
+  return a.dof == 0 && a.nchains <= 1024;
+}
+
 template <class TGT, class RNG>
 static int rwm_launch_d(const RwmArgs &a) {
+  if (rwm_use_spec(a)) {
+    const unsigned g = (unsigned)a.nchains;
+    if constexpr (std::is_same<TGT, CoalTarget>::value) {
+      rwm_spec_kernel<AMX_MAX_DIM, TGT, RNG><<<g, 32, 0, stream()>>>(a);
+    } else {
+      if (a.d <= 2) rwm_spec_kernel<2, TGT, RNG><<<g, 32, 0, stream()>>>(a);
+      else if (a.d <= 8) rwm_spec_kernel<8, TGT, RNG><<<g, 32, 0, stream()>>>(a);
+      else rwm_spec_kernel<AMX_MAX_DIM, TGT, RNG><<<g, 32, 0, stream()>>>(a);
+    }
+    count_launch();
+    AMX_CUDA(cudaGetLastError());
+    return AMX_OK;
+  }
   const unsigned grid = (unsigned)((a.nchains + kRwmThreads - 1) / kRwmThreads);
   if constexpr (std::is_same<TGT, CoalTarget>::value) {
     rwm_adapt_kernel<AMX_MAX_DIM, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);

@@ -107,3 +107,27 @@ def test_student_t_proposals_against_oracle(amx, orc, ht):
     assert np.array_equal(rep_dev, rep_orc)
     assert _rel(r["samples"][0], o["samples"]) < 1e-9 and _rel(r["sig"][0], o["sig"]) < 1e-9
     amx.rwm_adapt(T, 0, 1000, 1, init[:1], dof=0)  # leave the process-wide setting at its default
+
+
+@pytest.mark.parametrize("name,k", [("toy1", 1), ("toy2", 3), ("coalmine", 2), ("coalmine", 5), ("c1_normal", 0)])
+def test_speculative_kernel_is_the_sequential_chain(amx, name, k, monkeypatch):
+    """The warp-per-chain kernel (decision tree of the next five steps evaluated at once) and the
+    thread-per-chain kernel run the same chain: bit-identical samples, scales and traces on Philox streams."""
+    wl = cases.workload(name)
+    dims = np.asarray(wl["dims"])
+    d = int(dims[k])
+    init_all = cases.default_init(wl, 8)
+    off = int(dims[:k].sum())
+    init = init_all[off:off + d]
+    T = amx.Target(wl["target"])
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AMX_RWM_SPEC", mode)
+        out[mode] = amx.rwm_adapt(T, k, 1000, 3, init, seed=77)
+    a, b = out["1"], out["0"]
+    assert np.array_equal(a["samples"], b["samples"])
+    assert np.array_equal(a["sig"], b["sig"])
+    assert np.array_equal(a["sig_trace"], b["sig_trace"])
+    assert np.array_equal(a["acc_trace"], b["acc_trace"], equal_nan=True)
+    assert len(np.unique(a["samples"][0], axis=0)) > 100  # the chain moves
+    print(f"{name} k={k} d={d}: speculative {a['kernel_ms']:.0f} ms, sequential {b['kernel_ms']:.0f} ms")
