@@ -261,42 +261,67 @@ __global__ void __launch_bounds__(32) rwm_spec_kernel(RwmArgs a) {
 #pragma unroll
           for (int i = 0; i < DMAX; i++) cur[i] = xc[i];
           lp = lpn;
+        } else {
+#pragma unroll
+          for (int i = 0; i < DMAX; i++) xc[i] = cur[i];
         }
         end_of_sweep(sweep);
         sweep++;
         continue;
       }
     }
-    // how many coordinate steps the window holds: it may run into the following sweeps, and stops in front of a
-    // block-move sweep (whose first uniform is then read again at the top) and at the end of the schedule
+    // The window: up to five coordinate steps from (sweep, j); it may run into the following sweeps, and stops in
+    // front of a block-move sweep (whose first uniform is then read again at the top) and at the end of the
+    // schedule.  Per step: coordinate, sweep, adaptation gain and position in the uniform stream.  The loops over
+    // the window are fully unrolled so that these small arrays are registers.
+    int cq[kSpecDepth], sq[kSpecDepth];
+    unsigned long long nq[kSpecDepth];
+    double gq[kSpecDepth];
     int m = 0;
     {
       int s2 = sweep, j2 = j;
       unsigned long long n2 = n;
-      while (m < kSpecDepth) {
-        if (j2 == 0 && m > 0) {
-          if (s2 > a.nsweepr) break;
-          const double uu2 = u.at(n2);
-          if (s2 > a.nburn && uu2 < 0.1) break;
-          n2++;
+      bool open = true;
+#pragma unroll
+      for (int t = 0; t < kSpecDepth; t++) {
+        if (open && j2 == 0 && t > 0) {
+          if (s2 > a.nsweepr) {
+            open = false;
+          } else {
+            const double uu2 = u.at(n2);
+            if (s2 > a.nburn && uu2 < 0.1) open = false;
+            else n2++;
+          }
         }
-        n2 += 3;
-        m++;
-        if (++j2 == d) {
-          j2 = 0;
-          s2++;
+        cq[t] = j2;
+        sq[t] = s2;
+        nq[t] = n2;
+        gq[t] = 0.0;
+        if (open) {
+          gq[t] = a.gtab[s2 - 1];
+          n2 += 3;
+          m = t + 1;
+          if (++j2 == d) {
+            j2 = 0;
+            s2++;
+          }
         }
       }
+      sweep = s2;  // the chain's position after the window
+      j = j2;
+      n = n2;
     }
-    // step t of the window: coordinate, sweep and position in the uniform stream
-    auto coord_of = [&](int t) { return (j + t) % d; };
-    auto sweep_of = [&](int t) { return sweep + (j + t) / d; };
-    auto first_uniform_of = [&](int t) { return n + 3ull * (unsigned long long)t + (unsigned long long)((j + t) / d); };
+    auto pick_n = [&](int t) {
+      unsigned long long r = nq[0];
+#pragma unroll
+      for (int q = 1; q < kSpecDepth; q++) r = (t == q) ? nq[q] : r;
+      return r;
+    };
 
     // proposal noise of the window: lane t draws step t's variate (gauss(), :1639-1661), everyone gets all of them
     double zmine = 0.0;
     if (lane < m) {
-      const unsigned long long nt = first_uniform_of(lane);
+      const unsigned long long nt = pick_n(lane);
       const double ua = u.at(nt), ub = u.at(nt + 1);
       zmine = sqrt(-2.0 * log(ua)) * sin(6.283185307179586476925 * ub);
     }
@@ -304,28 +329,35 @@ __global__ void __launch_bounds__(32) rwm_spec_kernel(RwmArgs a) {
 #pragma unroll
     for (int t = 0; t < kSpecDepth; t++) z[t] = __shfl_sync(full, zmine, t);
 
-    // replay the prefix of this lane's node, then evaluate its proposal
+    // replay the prefix of this lane's node on its mirror of the state (xc, sg), evaluate its proposal, and put
+    // the touched entries back
     const bool node = t_me < m;
     double lpn = 0.0;
     if (node) {
 #pragma unroll
-      for (int i = 0; i < DMAX; i++) {
-        xc[i] = cur[i];
-        sg[i] = sig[i];
-      }
-      for (int q = 0; q < t_me; q++) {
-        const int c = coord_of(q);
-        const double si = aget(sg, c), gam = a.gtab[sweep_of(q) - 1];
-        if ((p_me >> q) & 1) {
-          aset(xc, c, fma(si, aget(z, q), aget(xc, c)));
-          aset(sg, c, max_m(0.0, si - gam * (alphastar - 1.0)));
-        } else {
-          aset(sg, c, max_m(0.0, si - gam * alphastar));
+      for (int q = 0; q < kSpecDepth; q++) {
+        if (q < t_me) {
+          const int c = cq[q];
+          const double si = aget(sg, c);
+          if ((p_me >> q) & 1) {
+            aset(xc, c, fma(si, z[q], aget(xc, c)));
+            aset(sg, c, max_m(0.0, si - gq[q] * (alphastar - 1.0)));
+          } else {
+            aset(sg, c, max_m(0.0, si - gq[q] * alphastar));
+          }
+        } else if (q == t_me) {
+          const int c = cq[q];
+          aset(xc, c, fma(aget(sg, c), z[q], aget(xc, c)));
         }
       }
-      const int c = coord_of(t_me);
-      aset(xc, c, fma(aget(sg, c), aget(z, t_me), aget(xc, c)));
       lpn = T.template eval<DMAX>(k, xc);
+#pragma unroll
+      for (int q = 0; q < kSpecDepth; q++)
+        if (q <= t_me) {
+          const int c = cq[q];
+          aset(xc, c, aget(cur, c));
+          aset(sg, c, aget(sig, c));
+        }
     }
     // the log-posterior of the node's current state: its last accepted ancestor's proposal, else the chain's
     int src = lane;
@@ -337,34 +369,40 @@ __global__ void __launch_bounds__(32) rwm_spec_kernel(RwmArgs a) {
     const double lpc = (p_me != 0) ? lpa : lp;
     int dec = 0;
     if (node) {
-      const double uacc = u.at(first_uniform_of(t_me) + 2);
+      const double uacc = u.at(pick_n(t_me) + 2);
       const double acc = min_m(1.0, mh_prob(lpn - lpc));  // :627
       dec = (uacc < acc) ? 1 : 0;
     }
     // walk the true path
     int path = 0;
-    for (int t = 0; t < m; t++) path |= __shfl_sync(full, dec, (1 << t) - 1 + path) << t;
-    // commit it: every lane applies the same m steps (:628-640)
-    for (int t = 0; t < m; t++) {
-      const int c = coord_of(t), sw = sweep_of(t);
-      const double si = aget(sig, c), gam = a.gtab[sw - 1];
-      const double lpt = __shfl_sync(full, lpn, (1 << t) - 1 + (path & ((1 << t) - 1)));
-      if ((path >> t) & 1) {
-        nacc[c]++;
-        ntry[c]++;
-        aset(cur, c, fma(si, aget(z, t), aget(cur, c)));
-        lp = lpt;
-        aset(sig, c, max_m(0.0, si - gam * (alphastar - 1.0)));
-      } else {
-        ntry[c]++;
-        aset(sig, c, max_m(0.0, si - gam * alphastar));
+#pragma unroll
+    for (int t = 0; t < kSpecDepth; t++)
+      if (t < m) path |= __shfl_sync(full, dec, (1 << t) - 1 + path) << t;
+    // commit it: every lane applies the same m steps to the state and to its mirror (:628-640)
+#pragma unroll
+    for (int t = 0; t < kSpecDepth; t++) {
+      if (t < m) {
+        const int c = cq[t];
+        const double si = aget(sig, c);
+        const double lpt = __shfl_sync(full, lpn, (1 << t) - 1 + (path & ((1 << t) - 1)));
+        double sn;
+        if ((path >> t) & 1) {
+          nacc[c]++;
+          ntry[c]++;
+          const double xn = fma(si, z[t], aget(cur, c));
+          aset(cur, c, xn);
+          aset(xc, c, xn);
+          lp = lpt;
+          sn = max_m(0.0, si - gq[t] * (alphastar - 1.0));
+        } else {
+          ntry[c]++;
+          sn = max_m(0.0, si - gq[t] * alphastar);
+        }
+        aset(sig, c, sn);
+        aset(sg, c, sn);
+        if (c == d - 1) end_of_sweep(sq[t]);
       }
-      if (c == d - 1) end_of_sweep(sw);
     }
-    const int q = j + m;
-    n += 3ull * (unsigned long long)m + (unsigned long long)((j + m - 1) / d);
-    sweep += q / d;
-    j = q % d;
   }
   if (lane == 0)
     for (int q = 0; q < d; q++) a.sig_out[(size_t)id * d + q] = sig[q];
