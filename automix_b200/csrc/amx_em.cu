@@ -45,7 +45,8 @@ constexpr int kEmTriMax = kEmDmax * (kEmDmax + 1) / 2;
 constexpr int kEmRecMax = AMX_REC_HEAD + 2 * kEmDmax + kEmTriMax;
 constexpr int kEmNV = kEmTriMax;  // values per CTA partial row (>= Lmax + Dmax + 2)
 
-enum EmPass { kPassInitStats = 0, kPassInitDens, kPassScatter, kPassDensRefresh, kPassRefresh, kPassStop };
+// kPassRefresh0 is the first E-step: the reference forms those responsibilities WITHOUT its `sum > 0` guard (:737-745)
+enum EmPass { kPassInitStats = 0, kPassInitDens, kPassScatter, kPassDensRefresh, kPassRefresh, kPassRefresh0, kPassStop };
 
 struct EmCtrl {
   unsigned int arrive, gen;
@@ -474,7 +475,7 @@ __device__ void em_leader_block(EmCtrl *c, const EmArgs &a, int pass, const doub
       } else {
         S.next = 0;
         S.iters = 0;  // the refresh that follows is the initial E-step (:733-744)
-        S.pass = kPassRefresh;
+        S.pass = kPassRefresh0;
       }
     }
     for (int q = t; q < tri; q += blockDim.x) S.Bc[q] = ld_cg(&c->B[0][q]);  // all start factors are equal
@@ -736,6 +737,26 @@ __device__ __forceinline__ void scatter_rows(double (&acc)[NACC], const double *
   }
 }
 
+// Log-density of one tile column under component l, operation for operation the reference's lnormprob
+// (automix.c:1727-1750: forward substitution with divisions, log of the product of the diagonal), from the
+// component's parameters in the control block.  Used only for the rare samples that every component puts below
+// exp(-667): there the cached exp(lpd) is (nearly) subnormal and lam * exp(lpd) no longer tracks the reference's
+// exp(log(lam) + lpd).
+__device__ __noinline__ double lnormprob_slow(const EmCtrl *c, int l, int d, const double *xcol) {
+  double r[kEmDmax];
+  double det = 1.0;
+  for (int i = 0; i < d; i++) r[i] = xcol[i * (kEmThreads + 4)] - ld_cg(&c->mu[l][i]);
+  for (int i = 0; i < d; i++) {
+    for (int j = 0; j < i; j++) r[i] -= ld_cg(&c->B[l][AMX_TRI(i, j)]) * r[j];
+    const double bii = ld_cg(&c->B[l][AMX_TRI(i, i)]);
+    r[i] /= bii;
+    det *= bii;
+  }
+  double q = 0.0;
+  for (int i = 0; i < d; i++) q += r[i] * r[i];
+  return -0.5 * q - (d / 2.0) * log(2.0 * 3.14159265358979323846) - log(det);
+}
+
 // ---- the fit kernel -------------------------------------------------------------------------------------
 // 128 threads per CTA, one tile = 128 samples.  Shared-memory tile rows (stride kEmTS doubles):
 //   xs[d]  sample coordinates     Es[Lmax]  density cache rows of the live components (component order)
@@ -965,10 +986,14 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         part_col[(size_t)q * pstride] = tot;
       }
       }
-    } else if (pass == kPassDensRefresh || pass == kPassRefresh) {
+    } else if (pass == kPassDensRefresh || pass == kPassRefresh || pass == kPassRefresh0) {
       // ---- (new density column,) responsibilities, column sums, log-likelihood, next first moment
-      const int L = s_L, nx = s_next, cc = s_c;
+      // When every density underflows the fit annihilates all of its components, and the reference then keeps
+      // "annihilating" into negative component counts until the iteration cap (:893-923 with Lkk == 0; the minimum
+      // so far is what it returns).  The leader mirrors that, the data pass sees an empty mixture.
+      const int L = s_L < 0 ? 0 : s_L, nx = s_next, cc = s_c;
       const bool dens = (pass == kPassDensRefresh);
+      const bool unguarded = (pass == kPassRefresh0);
       const int cslot = dens ? s_slot[cc] : 0;
       const int col = t >> 2, prt = t & 3;  // reduction role: 32 columns x 4 partial sums
       double acc_col = 0.0, acc_s1 = 0.0, ll = 0.0, nfb = 0.0;
@@ -1043,7 +1068,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
         // components are in flight at a time, the additions stay sequential
         double *__restrict__ Ecol = Es + t;
         const double *__restrict__ lam = s_lam;
-        double sum = 0.0;
+        double sum = 0.0, emax = 0.0;
         int l = 0;
         for (; l + 4 <= L; l += 4) {
           const double e0 = Ecol[(l + 0) * kEmTS], e1 = Ecol[(l + 1) * kEmTS], e2 = Ecol[(l + 2) * kEmTS],
@@ -1053,10 +1078,38 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
           sum = fma(a1, e1, sum);
           sum = fma(a2, e2, sum);
           sum = fma(a3, e3, sum);
+          emax = fmax(fmax(emax, fmax(e0, e1)), fmax(e2, e3));
         }
-        for (; l < L; l++) sum = fma(lam[l], Ecol[l * kEmTS], sum);
-        if (valid) {
-          if (sum > 0) {  // the reference's guard (:855-866)
+        for (; l < L; l++) {
+          const double e = Ecol[l * kEmTS];
+          sum = fma(lam[l], e, sum);
+          emax = fmax(emax, e);
+        }
+        if (valid && unguarded) {
+          // First E-step: w = lam * pdf / sum with no look at the sum, as the reference does (:737-745).  A sample
+          // that every start component misses gives 0/0 = NaN, which poisons the column sums; components are then
+          // annihilated until the (guarded) refresh after an annihilation clears it -- the reference's own path.
+          for (l = 0; l < L; l++) Ecol[l * kEmTS] = (lam[l] * Ecol[l * kEmTS]) / sum;
+        } else if (valid) {
+          if (emax < 1e-290 && L > 0) {
+            // Every component puts this sample below exp(-667): the cached densities are subnormal or zero, and
+            // lam * exp(lpd) no longer tracks the reference's exp(log(lam) + lpd) (nor can 1/sum be formed).
+            // Redo the sample the reference's way from the components' parameters (:849-866).
+            double s2 = 0.0;
+            for (l = 0; l < L; l++) {
+              const double wl = exp(log(lam[l]) + lnormprob_slow(ctrl, l, d, xs + t));
+              Ecol[l * kEmTS] = wl;
+              s2 += wl;
+            }
+            if (s2 > 0) {
+              for (l = 0; l < L; l++) Ecol[l * kEmTS] /= s2;
+              ll += log(s2);
+            } else {
+              nfb += 1.0;
+              const double w = 1.0 / L;
+              for (l = 0; l < L; l++) Ecol[l * kEmTS] = w;
+            }
+          } else if (sum > 0) {  // the reference's guard (:855-866)
             const double inv = 1.0 / sum;
             ll += log(sum);
             l = 0;
@@ -1181,7 +1234,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && a.rank == 0) {
       atomicAdd((unsigned long long *)&ctrl->dbg[0], (unsigned long long)(tk1 - tk0));
       if (pass == kPassScatter) atomicAdd((unsigned long long *)&ctrl->dbg[6], (unsigned long long)(tk1 - tk0));
-      if (pass == kPassDensRefresh || pass == kPassRefresh) atomicAdd((unsigned long long *)&ctrl->dbg[7], (unsigned long long)(tk1 - tk0));
+      if (pass == kPassDensRefresh || pass == kPassRefresh || pass == kPassRefresh0) atomicAdd((unsigned long long *)&ctrl->dbg[7], (unsigned long long)(tk1 - tk0));
     }
     const long long tk2 = clock64();
     // ------------------------------------------------------------------ reload the control state

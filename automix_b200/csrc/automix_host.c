@@ -669,6 +669,10 @@ int amx_sampler_set_seed(amSampler *am, uint64_t seed) {
   sampler_ext *e = ext_of(am, 1);
   e->seed = seed;
   e->seed_set = 1;
+  /* the start rows of the mixture fit come from the library's sdrand stream (:682-697), which initAMSampler seeds
+   * from the clock: reseed it too, so that a seeded run is reproducible end to end */
+  unsigned long s = (unsigned long)(seed ? seed : 1u);
+  sdrni(&s);
   return AMX_OK;
 }
 int amx_sampler_posterior(const amSampler *am, int model, unsigned long long *count, double *mean, double *cov,

@@ -195,7 +195,8 @@ int amx_sampler_set_target(amSampler *am, const struct amx_target *t);
  * stored samples are pooled for the fit (default 1 = the reference's single chain). */
 int amx_sampler_set_chains(amSampler *am, long rj_chains, long rwm_chains);
 /* Seed of the counter-based per-chain streams (default: am->seed, which initAMSampler takes
- * from the clock as the reference does). */
+ * from the clock as the reference does).  Also reseeds the library's sdrand() stream, which draws
+ * the start rows of the mixture fit, so a seeded run is reproducible end to end. */
 int amx_sampler_set_seed(amSampler *am, uint64_t seed);
 const amx_sampler_stats *amx_sampler_stats_get(const amSampler *am);
 /* Per-model posterior moments over the population after rjmcmc_samples: one draw per chain (its final

@@ -139,3 +139,65 @@ def test_rejects_bad_arguments(amx):
         amx.em_fit(x, np.arange(30, dtype=np.int32), Lmax=30)  # fewer samples than components
     with pytest.raises(amx.AmxError):
         amx.em_fit(np.zeros((100, 2)), np.zeros(4, np.int32), Lmax=4)  # duplicate start rows
+
+
+def _outlier_samples(d, n=2920, R=1000.0, seed=3):
+    """A unit Gaussian cloud plus two far points: under the single component the fit ends with, the outliers'
+    log-density is about -733, i.e. exp() of it is subnormal."""
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(n, d))
+    x[7, 0] = R
+    x[1900, 0] = -R
+    return x
+
+
+@pytest.mark.parametrize("d,Lmax", [(1, 3), (2, 3), (3, 6)])
+def test_subnormal_tail_densities(amx, orc, d, Lmax):
+    """Regression: responsibilities of samples whose total density is subnormal.  Multiplying by 1/sum overflows
+    there (the weight became inf, the column sum inf, the last component was annihilated and the fit ran on with
+    an empty mixture); the reference divides (:857-861) and gets exactly 1 with one component left."""
+    x = _outlier_samples(d)
+    orc.tape(cases.tape(55, 4096))
+    o = orc.fit_mixture(x, Lmax=Lmax, maxit=40, want_state=True)
+    assert o["cur_lpd"].min() < -709.0, "the case must reach the subnormal range to test anything"
+    g = amx.em_fit(x, o["init_idx"], Lmax=Lmax, maxit=40, want_state=True)
+    assert g["iters"] == o["iters"] and g["L"] == o["L"] == 1
+    assert np.array_equal(g["trace_L"], o["trace_L"]) and np.array_equal(g["trace_ann"], o["trace_ann"])
+    assert np.all(np.isfinite(g["cur_w"])) and np.allclose(g["cur_w"].sum(0), o["cur_w"].sum(0), rtol=1e-12)
+    assert np.max(np.abs(g["trace_loglik"] - o["trace_loglik"]) / np.abs(o["trace_loglik"])) < 1e-12
+    assert np.max(np.abs(g["mu"] - o["mu"])) < 1e-9 and np.max(np.abs(g["B"] - o["B"]) / np.maximum(1e-300, np.abs(o["B"]))) < 1e-10
+
+
+def test_ill_scaled_chain_samples_against_oracle(amx, orc):
+    """Stage-2 input as the coal-mining pipeline produces it: 13 coordinates whose scales differ by 1e6, a chain
+    with log-densities down to -1000 under the fitted components.  Several start-row draws, each compared with
+    the oracle iteration by iteration (this is where the empty-mixture runaway above was found: the reference
+    itself keeps 'annihilating' below zero components once a fit has lost all of them, :893-923, so a negative
+    count in a trace is legal -- it just has to be the reference's)."""
+    from automix_b200 import workloads as W
+
+    wl = W.coalmine()
+    T = amx.Target(wl["target"])
+    k = 5
+    d = int(wl["dims"][k])
+    off = int(np.sum(wl["dims"][:k]))
+    x = amx.rwm_adapt(T, k, 1000, 1, wl["init"][off:off + d], seed=1851 + 7919 * k)["samples"][0]
+    assert x.shape == (13000, 13) and np.isfinite(x).all()
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        idx = []
+        while len(idx) < 30:
+            v = int(np.floor(len(x) * rng.random()))
+            if v not in idx:
+                idx.append(v)
+        idx = np.array(idx)
+        orc.tape(np.concatenate([(idx + 0.5) / len(x), np.full(64, 0.5)]))  # the draws that select these rows
+        o = orc.fit_mixture(x, Lmax=30, maxit=60)
+        assert np.array_equal(o["init_idx"], idx)
+        g = amx.em_fit(x, idx, Lmax=30, maxit=60)
+        assert g["iters"] == o["iters"], (seed, g["iters"], o["iters"])
+        assert np.array_equal(g["trace_L"], o["trace_L"]), (seed, g["trace_L"], o["trace_L"])
+        assert np.array_equal(g["trace_ann"], o["trace_ann"]), seed
+        rel = np.abs(g["trace_loglik"] - o["trace_loglik"]) / np.maximum(1.0, np.abs(o["trace_loglik"]))
+        assert rel.max() < 1e-9, (seed, rel.max())
+        assert g["L"] == o["L"] and np.max(np.abs(g["lam"] - o["lam"])) < 1e-9
