@@ -1326,6 +1326,15 @@ __global__ void __launch_bounds__(256) autorj_generic_kernel(int d, long n, cons
 
 using namespace amx;
 
+// bytes of tile memory the aliased scratch of em_fit_kernel<DMAX> needs: s_red | s_tot | pad | LeaderS
+template <int DMAX>
+constexpr size_t em_scratch_bytes() {
+  constexpr int TRI = DMAX * (DMAX + 1) / 2;
+  constexpr int NRED = TRI > 2 * DMAX ? TRI : 2 * DMAX;
+  constexpr int NTOT = kEmLmax + 2 + DMAX + TRI;
+  return sizeof(double) * (size_t)(kEmWarps * NRED + NTOT + 1) + sizeof(LeaderS<DMAX>) + 16;
+}
+
 template <int DMAX>
 static int em_occupancy(size_t smem, int *per_sm) {
   AMX_CUDA(cudaFuncSetAttribute(em_fit_kernel<DMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1388,7 +1397,11 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   const char *fu = getenv("AMX_EM_FUSED");
   const int fused = (d <= 12 && use_tma && nbuf == 1) ? (fu ? (atoi(fu) != 0) : 1) : 0;  // entries e, e+64 cover tri(12) = 78
   size_t smem = nbuf * sizeof(double) * (size_t)(d + Lmax + 1 + (fused ? d : 0)) * kEmTS;
-  if (smem < 24 * 1024) smem = 24 * 1024;  // room for the leader's state, which aliases the tile
+  {  // room for the reduction scratch and the leader's state, which alias the tile (see em_fit_kernel)
+    const size_t need = d <= 4 ? em_scratch_bytes<4>() : d <= 8 ? em_scratch_bytes<8>() : d <= 12 ? em_scratch_bytes<12>()
+                        : d <= 20 ? em_scratch_bytes<20>() : em_scratch_bytes<32>();
+    if (smem < need) smem = need;
+  }
 
   EmArgs A[kEmMaxDev];
   cudaStream_t st[kEmMaxDev];

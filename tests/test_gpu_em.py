@@ -84,7 +84,8 @@ def test_product_sized_fit_against_reference_golden(amx, name, k):
 
 
 @pytest.mark.parametrize("d,n,L", [(1, 3000, 8), (4, 5000, 10), (7, 6000, 12), (10, 20000, 30), (12, 9000, 16),
-                                   (13, 6000, 10), (20, 8000, 12), (32, 4000, 6)])
+                                   (13, 6000, 10), (20, 8000, 12), (32, 4000, 6),
+                                   (24, 900, 2), (32, 600, 2), (17, 700, 3)])  # tile smaller than the aliased scratch
 def test_shapes_against_oracle(amx, orc, d, n, L):
     rng = np.random.default_rng(d)
     cents = rng.normal(size=(3, d)) * 4
