@@ -59,16 +59,45 @@ def test_trace_chain_against_reference_golden(amx, name):
     assert st["draws"] > 0
 
 
-@pytest.mark.parametrize("name,nchains,nsweeps", [("toy1", 64, 300), ("toy2", 48, 200), ("c5_rj", 40, 120), ("c1_normal", 33, 250), ("coalmine", 24, 150)])
+def _fitted_proposal(amx, wl):
+    """Stages 1-2 on the device, as the pipeline runs them: the proposal a real run jumps with (ill-scaled for the
+    coal-mining model: rates ~1e-3 next to change points ~1e4, components with log-densities far in the tail)."""
+    T = amx.Target(wl["target"])
+    dims = np.asarray(wl["dims"])
+    ncomp, wt, mean, tri, sig = [], [], [], [], []
+    off = 0
+    for k, d in enumerate(dims):
+        d = int(d)
+        r = amx.rwm_adapt(T, k, 1000, 1, wl["init"][off:off + d], seed=11 + k)
+        off += d
+        x = r["samples"][0]
+        idx, _ = amx.em_draw_init(len(x), 30, cases.tape(40 + k, 4096))
+        e = amx.em_fit(x, idx, Lmax=30, maxit=300)
+        assert 1 <= e["L"] <= 30
+        ncomp.append(e["L"])
+        wt.append(e["lam"])
+        mean.append(e["mu"].ravel())
+        tri.append(e["B"].ravel())
+        sig.append(r["sig"][0])
+    return dict(dims=dims.astype(np.int32), ncomp=np.array(ncomp, np.int32), wt=np.concatenate(wt),
+                mean=np.concatenate(mean), tri=np.concatenate(tri), sig=np.concatenate(sig))
+
+
+@pytest.mark.parametrize("name,nchains,nsweeps", [("toy1", 64, 300), ("toy2", 48, 200), ("c5_rj", 40, 120), ("c1_normal", 33, 250), ("coalmine", 24, 150),
+                                                  ("coalmine_fitted", 24, 160)])
 def test_population_against_oracle(amx, orc, ht, name, nchains, nsweeps):
     """Every chain gets its own tape; the oracle replays each chain on the CPU."""
+    fitted = name.endswith("_fitted")
+    name = name.replace("_fitted", "")
     wl = cases.workload(name)
     spec = wl["target"]
     ptr = ht.select(spec)
     dims = np.asarray(wl["dims"])
     dmax = int(dims.max())
     init = cases.default_init(wl, 5)
-    if spec["kind"] == "gaussmix":
+    if fitted:
+        mix = _fitted_proposal(amx, wl)
+    elif spec["kind"] == "gaussmix":
         from automix_b200 import workloads as W
 
         mix = W.ideal_proposal(wl)
