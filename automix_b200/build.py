@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libautomix.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CC = os.environ.get("CC", "gcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INC, "-I", CSRC] + ARCH
+NVFLAGS = [f"-D{d}" for d in os.environ.get("AMX_NVCC_DEFS", "").split()] + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INC, "-I", CSRC] + ARCH
 CFLAGS = ["-O2", "-fPIC", "-Wall", "-I", INC, "-I", CSRC]
 
 
