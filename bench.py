@@ -235,9 +235,9 @@ def main():
         roof_rj = {"bound": "fp64", "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                    "frac": ach / fp64_peak,
                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 chains (state load/store
-                   # only; independent of the number of sweeps): profiles/r01/ncu_rj_r01c.txt
-                   "traffic": 78.3e6 * (C / float(1 << 20)),
-                   "fp64_pipe_active_pct_ncu": 26.6,
+                   # only; independent of the number of sweeps): profiles/r01/ncu_rj_r01f.txt (67.2 + 19.1 MB)
+                   "traffic": 86.3e6 * (C / float(1 << 20)),
+                   "fp64_pipe_active_pct_ncu": 27.3,
                    "kernel": "rj_sweep_kernel", "launch_ms": st["kernel_ms"] / args.steps,
                    "flops_per_sweep": float(st["flops"]) / (C * S * args.steps),
                    "peak_source": "measured live with amx_measure_fp64_peak (dependent-free DFMA loop); "
@@ -326,9 +326,10 @@ def main():
                                      "inputs (80 MB) + density cache (240 MB) exceed L2, no flush needed"},
               "roofline": {"bound": "hbm", "achieved": alg_bytes / t_fit / 1e9, "peak": hbm, "unit": "GB/s",
                            "frac": alg_bytes / t_fit / 1e9 / hbm,
-                           # ncu: 28.35 GB (read+write) for 74 component steps + start-up at n=1e6, d=10
-                           # (profiles/r01/ncu_em_r01c.txt) -> 0.383 GB per component step, scaled to this launch
-                           "traffic": 0.383e9 * steps_ * (n / 1e6) * ((2 * d + L + 3) / 53.0),
+                           # ncu: 21.58 GB (read+write) for 74 component steps + start-up at n=1e6, d=10, L=30 with the
+                           # fused step (profiles/r01/ncu_em_r01f.txt) -> 0.292 GB per component step, scaled to
+                           # this launch by the rows a step streams (x, density cache, weights)
+                           "traffic": 0.292e9 * steps_ * (n / 1e6) * ((d + L + 2) / 42.0),
                            "kernel": "em_fit_kernel", "launch_ms": 1e3 * t_fit,
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                            "note": "algorithmic bytes = 8 d per sample-component-step (SURVEY.md 8d)",
