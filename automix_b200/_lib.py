@@ -40,7 +40,7 @@ _lib = None
 # every symbol include/amx.h declares (tests check that the library exports them all)
 EXPORTS = [
     "amx_last_error", "amx_version", "amx_device_count", "amx_set_device", "amx_set_stream",
-    "amx_synchronize", "amx_launch_count", "amx_measure_fp64_peak", "amx_mix_logpdf",
+    "amx_synchronize", "amx_set_deferred_sync", "amx_launch_count", "amx_measure_fp64_peak", "amx_mix_logpdf",
     "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
@@ -159,6 +159,11 @@ def set_stream(ptr: int | None):
 
 def synchronize():
     check(lib().amx_synchronize())
+
+
+def set_deferred_sync(on: bool):
+    """amx_set_deferred_sync: state transfers only enqueue; buffers must be pinned; sync before touching them."""
+    check(lib().amx_set_deferred_sync(int(bool(on))))
 
 
 def launch_count(reset=False) -> int:

@@ -15,6 +15,7 @@ namespace amx {
 
 static thread_local char g_err[512] = "";
 static cudaStream_t g_stream = nullptr;
+static int g_defer_sync = 0;
 static unsigned long long g_launches = 0;
 
 int fail(int code, const char *fmt, ...) {
@@ -25,6 +26,7 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 cudaStream_t stream() { return g_stream; }
+bool defer_sync() { return g_defer_sync != 0; }
 void count_launch(unsigned n) { g_launches += n; }
 
 int require_device() {
@@ -74,6 +76,10 @@ int amx_set_device(int ordinal) {
 }
 int amx_set_stream(void *s) {
   g_stream = reinterpret_cast<cudaStream_t>(s);
+  return AMX_OK;
+}
+int amx_set_deferred_sync(int on) {
+  g_defer_sync = on ? 1 : 0;
   return AMX_OK;
 }
 int amx_synchronize(void) {

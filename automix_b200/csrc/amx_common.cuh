@@ -12,6 +12,7 @@ namespace amx {
 // ---- host-side runtime state (amx_api.cu) -------------------------------------------
 int fail(int code, const char *fmt, ...);
 cudaStream_t stream();
+bool defer_sync();  // amx_set_deferred_sync: host-buffer state transfers only enqueue
 void count_launch(unsigned n = 1);
 int require_device();
 

@@ -871,7 +871,7 @@ int amx_rj_set_state(amx_rj *rj, long first, long count, const double *theta, co
   AMX_CUDA(cudaMemcpyAsync(s.k + first, k, sizeof(int) * count, cudaMemcpyHostToDevice, stream()));
   AMX_CUDA(cudaMemcpyAsync(s.nreinit + first, nreinit, sizeof(int) * count, cudaMemcpyHostToDevice, stream()));
   AMX_CUDA(cudaMemcpyAsync(s.pkllim + first, pkllim, sizeof(double) * count, cudaMemcpyHostToDevice, stream()));
-  AMX_CUDA(cudaStreamSynchronize(stream()));
+  if (!defer_sync()) AMX_CUDA(cudaStreamSynchronize(stream()));
   rj->sweep_i = sweep_i;
   return AMX_OK;
 }
@@ -897,11 +897,11 @@ int amx_rj_get_state(const amx_rj *rj, long first, long count, double *theta, do
     if (theta) AMX_CUDA(cudaMemcpyAsync(theta, th_cm, sizeof(double) * count * rj->dmax, cudaMemcpyDeviceToHost, stream()));
     if (pk) AMX_CUDA(cudaMemcpyAsync(pk, pk_cm, sizeof(double) * count * rj->nm, cudaMemcpyDeviceToHost, stream()));
   }
-  AMX_CUDA(cudaStreamSynchronize(stream()));
-  if (lp) AMX_CUDA(cudaMemcpy(lp, s.lp + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
-  if (k) AMX_CUDA(cudaMemcpy(k, s.k + first, sizeof(int) * count, cudaMemcpyDeviceToHost));
-  if (nreinit) AMX_CUDA(cudaMemcpy(nreinit, s.nreinit + first, sizeof(int) * count, cudaMemcpyDeviceToHost));
-  if (pkllim) AMX_CUDA(cudaMemcpy(pkllim, s.pkllim + first, sizeof(double) * count, cudaMemcpyDeviceToHost));
+  if (lp) AMX_CUDA(cudaMemcpyAsync(lp, s.lp + first, sizeof(double) * count, cudaMemcpyDeviceToHost, stream()));
+  if (k) AMX_CUDA(cudaMemcpyAsync(k, s.k + first, sizeof(int) * count, cudaMemcpyDeviceToHost, stream()));
+  if (nreinit) AMX_CUDA(cudaMemcpyAsync(nreinit, s.nreinit + first, sizeof(int) * count, cudaMemcpyDeviceToHost, stream()));
+  if (pkllim) AMX_CUDA(cudaMemcpyAsync(pkllim, s.pkllim + first, sizeof(double) * count, cudaMemcpyDeviceToHost, stream()));
+  if (!defer_sync()) AMX_CUDA(cudaStreamSynchronize(stream()));  // deferred: the caller owns pinned buffers and syncs
   if (sweep_i) *sweep_i = rj->sweep_i;
   return AMX_OK;
 }

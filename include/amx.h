@@ -50,6 +50,11 @@ int amx_set_device(int ordinal);
 /* Library work is enqueued on this stream (a cudaStream_t passed as void*;
  * NULL = the legacy default stream). */
 int amx_set_stream(void *cuda_stream);
+/* Deferred synchronisation for pipelines (default off).  When on, amx_rj_set_state and amx_rj_get_state only
+ * ENQUEUE their transfers on the current stream: the host buffers must be pinned and must not be touched until
+ * amx_synchronize() (or a sync of that stream) returns.  With two populations on two streams the transfers of
+ * one overlap the sweeps of the other. */
+int amx_set_deferred_sync(int on);
 int amx_synchronize(void);
 /* Kernels launched by this library since the counter was last reset. */
 unsigned long long amx_launch_count(int reset);

@@ -302,3 +302,53 @@ def test_student_t_and_permutation_modes_against_oracle(amx, orc, ht, dof, perm)
         _close(tr["lp"][c], r["lp"], "lp", 1e-11)
         _close(tr["theta"][c], r["theta"], "theta", 1e-11)
     assert st["draws"] + nchains == draws  # the oracle's count includes the chain-start uniform
+
+
+def test_deferred_sync_state_transfers(amx):
+    """amx_set_deferred_sync: set_state / get_state only enqueue; after amx_synchronize the (pinned) buffers hold
+    what the blocking calls return, and two populations on two streams can be driven from one host thread."""
+    import torch
+
+    from automix_b200 import workloads as W
+
+    wl = W.toy1()
+    mix = W.ideal_proposal(wl)
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    pops = [amx.RjPopulation(P, T, 4096, cases.default_init(wl, 5), seed=5 + q) for q in range(2)]
+    for p in pops:
+        p.init_chains()
+        p.sweeps(20, burning=True)
+    ref_states = [p.get_state() for p in pops]
+    streams = [torch.cuda.Stream() for _ in pops]
+    pins = []
+    for st in ref_states:
+        pin = {}
+        for key in ("theta", "pk", "lp", "k", "nreinit", "pkllim"):
+            t = torch.from_numpy(np.ascontiguousarray(st[key])).pin_memory()
+            pin[key], pin["_t_" + key] = t.numpy(), t
+        pins.append(pin)
+    try:
+        amx.set_deferred_sync(True)
+        for rep in range(3):
+            for p, pin, s, st in zip(pops, pins, streams, ref_states):
+                amx.set_stream(s.cuda_stream)
+                amx.synchronize()
+                p.set_state_arrays(pin, st["sweep_i"] + 10 * rep)
+                p.sweeps(10)
+                p.get_state(out=pin)
+        for s in streams:
+            amx.set_stream(s.cuda_stream)
+            amx.synchronize()
+    finally:
+        amx.set_deferred_sync(False)
+        amx.set_stream(None)
+    # the same 30 sweeps with blocking calls from the same start, on fresh populations with the same streams of uniforms
+    for q, (st, pin) in enumerate(zip(ref_states, pins)):
+        chk = amx.RjPopulation(P, T, 4096, cases.default_init(wl, 5), seed=5 + q)
+        chk.init_chains()
+        chk.sweeps(20, burning=True)
+        assert np.array_equal(chk.get_state()["theta"], st["theta"])
+        chk.sweeps(30)
+        want = chk.get_state()
+        for key in ("theta", "pk", "lp", "k"):
+            assert np.array_equal(pin[key], want[key]), key
