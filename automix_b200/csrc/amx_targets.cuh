@@ -156,8 +156,10 @@ struct CoalTarget {
       if (bad) return -10000.0;
       const double abcon = D[h->off[k] + 2];
       double lp = D[h->off[k] + 0];
+      double lh[8];  // log h_i: needed by the prior and again by the likelihood (one evaluation, same value)
       for (int i = 0; i <= ns; i++) {
-        lp += (abcon + (alpha - 1.0) * log(hh[i]) - beta * hh[i]);
+        lh[i] = log(hh[i]);
+        lp += (abcon + (alpha - 1.0) * lh[i] - beta * hh[i]);
         lp += log(ds[i]);
       }
       lp += D[h->off[k] + 1];
@@ -183,7 +185,7 @@ struct CoalTarget {
       if (regular) {
         idx[ns + 1] = AMX_COAL_N;
         double llh = 0.0;
-        for (int j = 0; j <= ns; j++) llh += ((idx[j + 1] - idx[j]) * log(hh[j]) - hh[j] * ds[j]);
+        for (int j = 0; j <= ns; j++) llh += ((idx[j + 1] - idx[j]) * lh[j] - hh[j] * ds[j]);
         return lp + llh;
       }
       int seen = 0, j = 0;
@@ -192,13 +194,13 @@ struct CoalTarget {
         if (c_coal_y[i] > top) {  // at most one segment advance per datum (usercpt.c:114-127)
           const int nj = i - seen;
           seen = i;
-          llh += (nj * log(hh[j]) - hh[j] * ds[j]);
+          llh += (nj * lh[j] - hh[j] * ds[j]);
           j++;
           if (j > ns) return lp;
           top = s[j + 1];
         }
       }
-      llh += (AMX_COAL_N - seen) * log(hh[j]) - hh[j] * ds[j];
+      llh += (AMX_COAL_N - seen) * lh[j] - hh[j] * ds[j];
       return lp + llh;
     }
   }
