@@ -107,6 +107,7 @@ struct EmArgs {
                 // so a component step is ONE pass and ONE barrier; 0: separate centred scatter pass
   int use_tma;  // 1: tile rows by cp.async.bulk + mbarrier; 0: coalesced per-thread loads into the tile
   int nbuf;  // tile buffers per CTA: 2 = fetch of tile k+1 overlaps tile k, 1 = more resident CTAs
+  int smem_doubles;  // dynamic shared memory of the launch, in doubles
   long n, npad;
   const double *x;  // n x d row-major (device)
   double *xT, *E, *wnxt;
@@ -128,9 +129,10 @@ __device__ __forceinline__ T ld_cg(const T *p) {
 // remote).  The last GPU's CTA is the leader: it sums the per-GPU rows through peer loads in GPU order,
 // runs the sequential section, pushes the public state and the release flags to every GPU with peer stores.
 // Counters only grow, so there are no reset races; waiters poll a flag in their own GPU's memory.
-__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot, double *s_chunk);
+__device__ __forceinline__ uint32_t smem_u32(const void *p);
+__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot, double *s_chunk, int chunk_cap);
 
-__device__ __forceinline__ int barrier_arrive(const EmArgs &a, unsigned &epoch, int nv, double *s_tot, double *s_chunk) {
+__device__ __forceinline__ int barrier_arrive(const EmArgs &a, unsigned &epoch, int nv, double *s_tot, double *s_chunk, int chunk_cap) {
   __shared__ int s_last;
   const EmDev &me = a.dev[a.rank];
   __syncthreads();
@@ -142,7 +144,7 @@ __device__ __forceinline__ int barrier_arrive(const EmArgs &a, unsigned &epoch, 
   }
   __syncthreads();
   if (!s_last) return 0;
-  if (nv > 0) leader_reduce(me.part, nv, s_tot, s_chunk);  // this GPU's CTAs, coalesced, fixed order
+  if (nv > 0) leader_reduce(me.part, nv, s_tot, s_chunk, chunk_cap);  // this GPU's CTAs, coalesced, fixed order
   if (a.ndev == 1) return 2;
   // The leader is always GPU 0's last CTA: the control block lives in GPU 0's memory, so the sequential
   // section runs on local memory; the other GPUs post their reduced row and a remote arrival and go to wait.
@@ -258,20 +260,60 @@ __device__ __forceinline__ void block_reduce_store(const double (&v)[NVAL], int 
 // that the 32 lanes of a warp read 32 CONSECUTIVE CTAs of one value: one coalesced 256-byte request instead
 // of 32 scattered sectors (the scattered form kept one SM's L1TEX busy for ~60k cycles per pass at 592 CTAs).
 // Lane sums run over b = lane, lane+32, ... and are combined by a fixed shuffle tree, so the order of
-// additions depends only on the launch geometry (bitwise reproducible).  Two values are in flight per warp.
-__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot, double *s_chunk) {
+// additions depends only on the launch geometry (bitwise reproducible).
+// One batch: NVB values x KB loads per lane, at most 20 doubles -- what the register budget of this kernel lets
+// ptxas keep in flight as ONE group.  (With 40 it issued 17 loads and then trickled the rest between dependent
+// adds: eight L2 round trips per batch.  The section is a chain of such round trips, ~150-200 ns each.)
+template <int NVB, int KB>
+__device__ __forceinline__ void leader_reduce_batch(const double *part, int G, int q0, int nv, double *s_tot) {
+  const int lane = threadIdx.x & 31;
+  double v[NVB][KB];
+#pragma unroll
+  for (int a = 0; a < NVB; a++) {
+    const int q = q0 + a;
+    const double *src = part + (size_t)(q < nv ? q : q0) * G;
+#pragma unroll
+    for (int k = 0; k < KB; k++) {
+      const int b = lane + 32 * k;
+      v[a][k] = (q < nv && b < G) ? ld_cg(src + b) : 0.0;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NVB; a++) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < KB; k++) t += v[a][k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0 && q0 + a < nv) s_tot[q0 + a] = t;
+  }
+}
+template <int NVB, int KB>
+__device__ __forceinline__ void leader_reduce_all(const double *part, int G, int nv, double *s_tot) {
+  const int warp = threadIdx.x >> 5;
+  for (int q = NVB * warp; q < nv; q += NVB * kEmWarps) leader_reduce_batch<NVB, KB>(part, G, q, nv, s_tot);
+}
+__device__ __forceinline__ void leader_reduce(const double *part, int nv, double *s_tot, double *s_chunk, int chunk_cap) {
   (void)s_chunk;
-  const int G = (int)gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int q = 2 * warp; q < nv; q += 2 * kEmWarps) {
-    const double *s0 = part + (size_t)q * G;
-    const bool two = (q + 1 < nv);
-    const double *s1 = part + (size_t)(two ? q + 1 : q) * G;
-    double t0 = 0.0, t1 = 0.0;
-    for (int base = 0; base < G; base += 32 * 20) {  // 20 x 2 independent loads in flight per lane
-      double v0[20], v1[20];
+  (void)chunk_cap;
+  const int G = (int)gridDim.x, kb = (G + 31) / 32;  // loads per value and lane
+  if (kb <= 2) leader_reduce_all<8, 2>(part, G, nv, s_tot);
+  else if (kb <= 4) leader_reduce_all<4, 4>(part, G, nv, s_tot);
+  else if (kb <= 5) leader_reduce_all<3, 5>(part, G, nv, s_tot);
+  else if (kb <= 8) leader_reduce_all<2, 8>(part, G, nv, s_tot);
+  else if (kb <= 10) leader_reduce_all<2, 10>(part, G, nv, s_tot);
+  else if (kb <= 20) {
+    // full grids (592 CTAs): two values x 20 loads per round measured best (16 us per barrier; one value x 20 loads:
+    // 17 us; staging whole values through shared memory with cp.async: 22 us)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 2 * warp; q < nv; q += 2 * kEmWarps) {
+      const double *s0 = part + (size_t)q * G;
+      const bool two = (q + 1 < nv);
+      const double *s1 = part + (size_t)(two ? q + 1 : q) * G;
+      double t0 = 0.0, t1 = 0.0, v0[20], v1[20];
 #pragma unroll
       for (int k = 0; k < 20; k++) {
-        const int b = base + lane + 32 * k;
+        const int b = lane + 32 * k;
         v0[k] = (b < G) ? ld_cg(s0 + b) : 0.0;
         v1[k] = (b < G) ? ld_cg(s1 + b) : 0.0;
       }
@@ -280,15 +322,25 @@ __device__ __forceinline__ void leader_reduce(const double *part, int nv, double
         t0 += v0[k];
         t1 += v1[k];
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      t0 += __shfl_xor_sync(0xffffffffu, t0, o);
-      t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+      }
+      if (lane == 0) {
+        s_tot[q] = t0;
+        if (two) s_tot[q + 1] = t1;
+      }
     }
-    if (lane == 0) {
-      s_tot[q] = t0;
-      if (two) s_tot[q + 1] = t1;
+  }
+  else {  // more CTAs than any current device holds: same order of additions, loads one by one
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < nv; q += kEmWarps) {
+      double t = 0.0;
+      for (int b = lane; b < G; b += 32) t += ld_cg(part + (size_t)q * G + b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) s_tot[q] = t;
     }
   }
   __syncthreads();
@@ -774,7 +826,8 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
   constexpr int NTOT = kEmLmax + 2 + DMAX + TRI;
   double *s_red = tile;                         // [kEmWarps * NRED]
   double *s_tot = tile + kEmWarps * NRED;       // [NTOT]
-  double *s_chunk = nullptr;
+  double *s_chunk = tile + kEmWarps * NRED + NTOT + (NTOT & 1);  // staging area of the partial reduce (idle tile memory)
+  const int chunk_cap = a.smem_doubles - (kEmWarps * NRED + NTOT + (NTOT & 1));
   LeaderS<DMAX> &s_lead = *reinterpret_cast<LeaderS<DMAX> *>(tile + kEmWarps * NRED + NTOT + (NTOT & 1));
   __shared__ double s_pivot[DMAX];
   __shared__ double s_rec[AMX_REC_HEAD + 2 * DMAX + TRI];
@@ -1211,7 +1264,7 @@ __global__ void __launch_bounds__(kEmThreads, 4) em_fit_kernel(EmArgs a) {
 
     // ------------------------------------------------------------------ barrier + leader
     const long long tk1 = clock64();
-    const int role = barrier_arrive(a, epoch, nv, s_tot, s_chunk);
+    const int role = barrier_arrive(a, epoch, nv, s_tot, s_chunk, chunk_cap);
     bool alive = true;
     if (role == 2) {
       const long long tl1 = clock64();
@@ -1467,6 +1520,7 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     a.maxit = maxit;
     a.use_tma = use_tma;
     a.nbuf = nbuf;
+    a.smem_doubles = (int)(smem / sizeof(double));
     a.fused = fused;
     a.n = off[g + 1] - off[g];
     a.npad = (a.n + kEmThreads - 1) / kEmThreads * kEmThreads;  // whole tiles; the padding is zero and carries no weight
