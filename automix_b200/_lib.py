@@ -40,7 +40,7 @@ _lib = None
 # every symbol include/amx.h declares (tests check that the library exports them all)
 EXPORTS = [
     "amx_last_error", "amx_version", "amx_device_count", "amx_set_device", "amx_set_stream",
-    "amx_synchronize", "amx_set_deferred_sync", "amx_launch_count", "amx_measure_fp64_peak", "amx_mix_logpdf",
+    "amx_synchronize", "amx_set_deferred_sync", "amx_release_workspace", "amx_launch_count", "amx_measure_fp64_peak", "amx_mix_logpdf",
     "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",

@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "amx_internal.cuh"
@@ -1420,6 +1421,78 @@ static int em_launch_d(int d, EmArgs &a, unsigned grid, size_t smem, cudaStream_
 // per GPU; every GPU runs the same persistent kernel on its shard and they meet at the cross-GPU barrier of
 // the kernel, exchanging only the per-pass partial sums (<= 2 KB per GPU) through peer memory.
 // x_host: n x d row-major host samples, or NULL with x_dev0 = device samples (ndev must be 1).
+// ---- workspace pool of the fit --------------------------------------------------------------------------------
+// A fit needs ~n (2d + Lmax + 2) doubles of device memory (400 MB for n = 1e6, d = 10, Lmax = 30); cudaMalloc and
+// cudaFree of blocks that size cost milliseconds each and synchronise the device, which is what an end-to-end
+// fit (host samples in, mixture out) was spending most of its non-kernel time on.  Blocks are therefore kept
+// after a fit and handed out again when a later fit asks for the same size on the same device; everything a
+// kernel reads before writing is initialised explicitly, as it was with fresh memory.  amx_release_workspace()
+// returns the idle blocks to the driver; at most 4 GB stay idle.
+namespace {
+struct WsBlock {
+  int dev;
+  size_t bytes;
+  void *p;
+};
+std::vector<WsBlock> g_ws_idle, g_ws_live;
+std::mutex g_ws_mu;
+constexpr size_t kWsIdleCap = (size_t)4 << 30;
+
+template <class T>
+cudaError_t ws_malloc(T **p, size_t bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  for (size_t i = 0; i < g_ws_idle.size(); i++)
+    if (g_ws_idle[i].dev == dev && g_ws_idle[i].bytes == bytes) {
+      *p = static_cast<T *>(g_ws_idle[i].p);
+      g_ws_live.push_back(g_ws_idle[i]);
+      g_ws_idle.erase(g_ws_idle.begin() + i);
+      return cudaSuccess;
+    }
+  void *q = nullptr;
+  e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return e;
+  *p = static_cast<T *>(q);
+  g_ws_live.push_back({dev, bytes, q});
+  return cudaSuccess;
+}
+
+void ws_trim_locked(size_t cap) {
+  size_t idle = 0;
+  for (const WsBlock &b : g_ws_idle) idle += b.bytes;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  while (idle > cap && !g_ws_idle.empty()) {  // oldest first
+    cudaSetDevice(g_ws_idle.front().dev);
+    cudaFree(g_ws_idle.front().p);
+    idle -= g_ws_idle.front().bytes;
+    g_ws_idle.erase(g_ws_idle.begin());
+  }
+  cudaSetDevice(cur);
+}
+
+void ws_free(const void *p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  for (size_t i = 0; i < g_ws_live.size(); i++)
+    if (g_ws_live[i].p == p) {
+      g_ws_idle.push_back(g_ws_live[i]);
+      g_ws_live.erase(g_ws_live.begin() + i);
+      ws_trim_locked(kWsIdleCap);
+      return;
+    }
+  cudaFree(const_cast<void *>(p));  // not ours
+}
+}  // namespace
+
+extern "C" int amx_release_workspace(void) {
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  ws_trim_locked(0);
+  return AMX_OK;
+}
+
 static int em_fit_general(int ndev, const int *devices, int d, long n, const double *x_host, const double *x_dev0,
                           int Lmax, int maxit, const int *init_idx, double *wt, double *mean, double *tri, int *trace_L,
                           double *trace_loglik, double *trace_cost, int *trace_ann, double *cur_wt, double *cur_mean,
@@ -1492,13 +1565,13 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
 
   // GPU 0: the control block, the traces and the start rows
   AMX_CUDA(cudaSetDevice(devs[0]));
-  AMX_CUDA(cudaMalloc(&ctrl, sizeof(EmCtrl)));
+  AMX_CUDA(ws_malloc(&ctrl, sizeof(EmCtrl)));
   AMX_CUDA(cudaMemset(ctrl, 0, sizeof(EmCtrl)));
-  AMX_CUDA(cudaMalloc(&init_rows, sizeof(double) * (size_t)Lmax * d));
-  AMX_CUDA(cudaMalloc(&tr_L, sizeof(int) * cap));
-  AMX_CUDA(cudaMalloc(&tr_ann, sizeof(int) * cap));
-  AMX_CUDA(cudaMalloc(&tr_ll, sizeof(double) * cap));
-  AMX_CUDA(cudaMalloc(&tr_cost, sizeof(double) * cap));
+  AMX_CUDA(ws_malloc(&init_rows, sizeof(double) * (size_t)Lmax * d));
+  AMX_CUDA(ws_malloc(&tr_L, sizeof(int) * cap));
+  AMX_CUDA(ws_malloc(&tr_ann, sizeof(int) * cap));
+  AMX_CUDA(ws_malloc(&tr_ll, sizeof(double) * cap));
+  AMX_CUDA(ws_malloc(&tr_cost, sizeof(double) * cap));
   for (int l = 0; l < Lmax; l++) {
     if (x_host)
       AMX_CUDA(cudaMemcpy(init_rows + (size_t)l * d, x_host + (size_t)init_idx[l] * d, sizeof(double) * d, cudaMemcpyHostToDevice));
@@ -1533,19 +1606,19 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     else AMX_CUDA(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
     if (x_host) {
       double *xs = nullptr;
-      AMX_CUDA(cudaMalloc(&xs, sizeof(double) * (size_t)a.n * d));
+      AMX_CUDA(ws_malloc(&xs, sizeof(double) * (size_t)a.n * d));
       AMX_CUDA(cudaMemcpyAsync(xs, x_host + (size_t)off[g] * d, sizeof(double) * (size_t)a.n * d, cudaMemcpyHostToDevice, st[g]));
       a.x = xs;
     } else {
       a.x = x_dev0;
     }
-    AMX_CUDA(cudaMalloc(&a.xT, sizeof(double) * (size_t)d * a.npad));
-    AMX_CUDA(cudaMalloc(&a.E, sizeof(double) * (size_t)Lmax * a.npad));
-    AMX_CUDA(cudaMalloc(&a.wnxt, sizeof(double) * (size_t)a.npad));
+    AMX_CUDA(ws_malloc(&a.xT, sizeof(double) * (size_t)d * a.npad));
+    AMX_CUDA(ws_malloc(&a.E, sizeof(double) * (size_t)Lmax * a.npad));
+    AMX_CUDA(ws_malloc(&a.wnxt, sizeof(double) * (size_t)a.npad));
     AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, st[g]));
     AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, st[g]));
     AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, st[g]));
-    if (cur_w) AMX_CUDA(cudaMalloc(&a.w_out, sizeof(double) * (size_t)a.n * Lmax));
+    if (cur_w) AMX_CUDA(ws_malloc(&a.w_out, sizeof(double) * (size_t)a.n * Lmax));
     int per_sm = 0;
     if ((rc = em_occupancy_d(d, smem, &per_sm))) return rc;
     if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM (%zu B of shared memory)", smem);
@@ -1554,11 +1627,11 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     EmDev dv;
     memset(&dv, 0, sizeof(dv));
     dv.grid = (int)grid;
-    AMX_CUDA(cudaMalloc(&dv.part, sizeof(double) * (size_t)grid * kEmNV));
-    AMX_CUDA(cudaMalloc(&dv.devrow, sizeof(double) * kEmNV));
-    AMX_CUDA(cudaMalloc(&dv.flags, sizeof(unsigned) * 8 * (size_t)grid));
-    AMX_CUDA(cudaMalloc(&dv.arrive, sizeof(unsigned) * 8));
-    AMX_CUDA(cudaMalloc(&dv.pub, sizeof(EmPublic)));
+    AMX_CUDA(ws_malloc(&dv.part, sizeof(double) * (size_t)grid * kEmNV));
+    AMX_CUDA(ws_malloc(&dv.devrow, sizeof(double) * kEmNV));
+    AMX_CUDA(ws_malloc(&dv.flags, sizeof(unsigned) * 8 * (size_t)grid));
+    AMX_CUDA(ws_malloc(&dv.arrive, sizeof(unsigned) * 8));
+    AMX_CUDA(ws_malloc(&dv.pub, sizeof(EmPublic)));
     AMX_CUDA(cudaMemsetAsync(dv.flags, 0, sizeof(unsigned) * 8 * (size_t)grid, st[g]));
     AMX_CUDA(cudaMemsetAsync(dv.arrive, 0, sizeof(unsigned) * 8, st[g]));
     AMX_CUDA(cudaMemsetAsync(dv.pub, 0, sizeof(EmPublic), st[g]));
@@ -1654,13 +1727,13 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   for (int g = 0; g < ndev; g++) {
     cudaSetDevice(devs[g]);
     EmArgs &a = A[g];
-    if (x_host) cudaFree(const_cast<double *>(a.x));
-    cudaFree(a.xT); cudaFree(a.E); cudaFree(a.wnxt); cudaFree(a.w_out);
-    cudaFree(a.dev[g].part); cudaFree(a.dev[g].devrow); cudaFree(a.dev[g].flags); cudaFree(a.dev[g].arrive); cudaFree(a.dev[g].pub);
+    if (x_host) ws_free(const_cast<double *>(a.x));
+    ws_free(a.xT); ws_free(a.E); ws_free(a.wnxt); ws_free(a.w_out);
+    ws_free(a.dev[g].part); ws_free(a.dev[g].devrow); ws_free(a.dev[g].flags); ws_free(a.dev[g].arrive); ws_free(a.dev[g].pub);
     if (!(g == 0 && ndev == 1)) cudaStreamDestroy(st[g]);
   }
   cudaSetDevice(devs[0]);
-  cudaFree(ctrl); cudaFree(init_rows); cudaFree(tr_L); cudaFree(tr_ann); cudaFree(tr_ll); cudaFree(tr_cost);
+  ws_free(ctrl); ws_free(init_rows); ws_free(tr_L); ws_free(tr_ann); ws_free(tr_ll); ws_free(tr_cost);
   cudaSetDevice(home);
   if (rc != AMX_OK) return rc;
   if (status == AMX_ECUDA) return fail(status, "EM fit: a GPU stopped answering at the cross-GPU barrier");

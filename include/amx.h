@@ -50,6 +50,9 @@ int amx_set_device(int ordinal);
 /* Library work is enqueued on this stream (a cudaStream_t passed as void*;
  * NULL = the legacy default stream). */
 int amx_set_stream(void *cuda_stream);
+/* The mixture fit keeps its device workspace (about n (2d + Lmax + 2) doubles) for the next fit of the same shape
+ * instead of returning it to the driver after every call; this hands the idle blocks back. */
+int amx_release_workspace(void);
 /* Deferred synchronisation for pipelines (default off).  When on, amx_rj_set_state and amx_rj_get_state only
  * ENQUEUE their transfers on the current stream: the host buffers must be pinned and must not be touched until
  * amx_synchronize() (or a sync of that stream) returns.  With two populations on two streams the transfers of
