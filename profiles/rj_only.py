@@ -11,8 +11,22 @@ if name in ("toy1", "toy2"):
     g = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", name + ".npz")))
     mix = {k[4:]: g[k] for k in g if k.startswith("mix_")}
     init = g["init"]
-else:
+elif wl["target"]["kind"] == "gaussmix":
     mix, init = W.ideal_proposal(wl), wl["init"]
+else:  # no closed-form proposal (coal-mining): run stages 1-2 on the device, as the pipeline does
+    T0 = amx.Target(wl["target"])
+    init = wl["init"]
+    ncomp, wt, mean, tri, sig, off = [], [], [], [], [], 0
+    for k, d in enumerate(wl["dims"]):
+        d = int(d)
+        r = amx.rwm_adapt(T0, k, 1000, 1, init[off:off + d], seed=11 + k)
+        off += d
+        xs = r["samples"][0]
+        idx, _ = amx.em_draw_init(len(xs), 30, W.splitmix_uniforms_fast(40 + k, 4096))
+        e = amx.em_fit(xs, idx, Lmax=30, maxit=300)
+        ncomp.append(e["L"]); wt.append(e["lam"]); mean.append(e["mu"].ravel()); tri.append(e["B"].ravel()); sig.append(r["sig"][0])
+    mix = dict(dims=np.asarray(wl["dims"], np.int32), ncomp=np.array(ncomp, np.int32), wt=np.concatenate(wt),
+               mean=np.concatenate(mean), tri=np.concatenate(tri), sig=np.concatenate(sig))
 T, P = amx.Target(wl["target"]), amx.Proposal(mix)
 pop = amx.RjPopulation(P, T, C, init, seed=1)
 pop.init_chains()
