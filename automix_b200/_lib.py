@@ -44,8 +44,8 @@ EXPORTS = [
     "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
-    "amx_rj_set_tape", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
-    "amx_rj_collect", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_sokal", "amx_sokal_dev", "amx_rj_sokal",
+    "amx_rj_set_tape", "amx_rj_set_pk_mode", "amx_rj_get_pk_shared", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
+    "amx_rj_collect", "amx_rj_visit_se", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_sokal", "amx_sokal_dev", "amx_rj_sokal",
     "amx_rj_moments_reset", "amx_rj_moments_accumulate", "amx_rj_moments_get", "amx_em_fit", "amx_em_fit_dev",
     "amx_em_draw_init", "amx_em_fit_multi", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
 ]
@@ -94,6 +94,8 @@ def lib():
     L.amx_rj_destroy.argtypes = [C.c_void_p]
     L.amx_rj_set_tape.argtypes = [C.c_void_p, _dp, C.c_long]
     L.amx_rj_set_chain_base.argtypes = [C.c_void_p, C.c_uint64]
+    L.amx_rj_set_pk_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.amx_rj_get_pk_shared.argtypes = [C.c_void_p, _dp, _ip, _dp]
     L.amx_rj_set_modes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.amx_rwm_set_dof.argtypes = [C.c_int]
     L.amx_copy_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -103,6 +105,7 @@ def lib():
     L.amx_rj_sweeps.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_int]
     L.amx_rj_collect.argtypes = [C.c_void_p, _u64p, C.POINTER(RjStats), C.c_int]
     L.amx_rj_get_trace.argtypes = [C.c_void_p, _ip, _dp, _dp, _dp]
+    L.amx_rj_visit_se.argtypes = [C.c_void_p, _dp, _dp, _ip]
     L.amx_sokal.argtypes = [C.c_int, C.c_long, _dp, _dp, _dp, _ip]
     L.amx_sokal_dev.argtypes = [C.c_int, C.c_long, C.c_void_p, _dp, _dp, _ip]
     L.amx_rj_sokal.argtypes = [C.c_void_p, C.c_long, _dp, _dp, _ip]
@@ -274,6 +277,16 @@ class RjPopulation:
     def set_modes(self, dof=0, do_perm=False):
         check(lib().amx_rj_set_modes(self.h, int(dof), int(do_perm)))
 
+    def set_pk_mode(self, population: bool, segment_sweeps: int = 0):
+        """amx_rj_set_pk_mode: per-chain pk adaptation (the reference's rule) or one pk shared by the population."""
+        check(lib().amx_rj_set_pk_mode(self.h, 1 if population else 0, int(segment_sweeps)))
+
+    def pk_shared(self):
+        pk = np.zeros(self.nm)
+        nre, lim = C.c_int(0), C.c_double(0)
+        check(lib().amx_rj_get_pk_shared(self.h, _d(pk), C.byref(nre), C.byref(lim)))
+        return pk, int(nre.value), float(lim.value)
+
     def set_chain_base(self, first_chain_id: int):
         check(lib().amx_rj_set_chain_base(self.h, int(first_chain_id)))
 
@@ -334,6 +347,12 @@ class RjPopulation:
         check(lib().amx_rj_collect(self.h, vis.ctypes.data_as(_u64p), C.byref(st), int(reset)))
         stats = {f: getattr(st, f) for f, _ in RjStats._fields_}
         return vis, stats
+
+    def visit_se(self):
+        """(p, se, ngroups) of the counts of the last collect(): standard error from the spread between groups of chains."""
+        p, se, g = np.zeros(self.nm), np.zeros(self.nm), C.c_int(0)
+        check(lib().amx_rj_visit_se(self.h, _d(p), _d(se), C.byref(g)))
+        return p, se, int(g.value)
 
     def trace(self):
         n = self.last_nsweeps

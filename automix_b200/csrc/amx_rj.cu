@@ -27,6 +27,58 @@ __global__ void rj_gamma_kernel(double *g, unsigned long long sweep0, int n) {
   if (i < n) g[i] = pow(1.0 / (double)(sweep0 + (unsigned long long)i + 1ull), (2.0 / 3.0));
 }
 
+// ---- population pk adaptation ------------------------------------------------------------------------------
+// The reference adapts the model-jump probabilities of ITS one chain by pk += gamma_t (1[k_t] - pk) after every
+// sweep (automix.c:1258-1282).  Run as thousands of short chains that rule is biased at finite time -- a chain's
+// pk is correlated with the chain's own recent path (measured with the reference itself, oracle/ref_population.c:
+// 500 chains x (2000 + 2000) sweeps give P(k=5) = 0.102 +- 0.002 on the coal-mining posterior where its single
+// long chain gives 0.115 and the same 500 chains without adaptation 0.118).  In the population mode every chain
+// proposes from ONE shared pk, and the indicator of the reference's rule is replaced by the population's occupancy:
+// the sweep kernels already accumulate the model-visit histogram with warp-aggregated atomics; after a segment of m
+// sweeps this kernel applies the m per-sweep updates with that segment's visit fractions f in place of 1[k],
+//     pk <- prod(1 - gamma_t) pk + (1 - prod(1 - gamma_t)) f,
+// followed by the reference's re-initialisation rule (any pk < pkllim -> uniform, pkllim = 1/(10 nreinit)).
+// Within a segment pk is constant, so every sweep is a Metropolis-Hastings kernel that leaves the posterior
+// invariant: the estimator is unbiased whatever the segment's statistics are.
+struct RjPkShared {
+  double pk[AMX_MAX_MODELS];
+  double pkllim;
+  int nreinit;
+  unsigned long long prev[AMX_MAX_MODELS];  // visit histogram at the previous update
+};
+__global__ void rj_pk_reset_kernel(RjPkShared *ps, int nm) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int j = 0; j < AMX_MAX_MODELS; j++) ps->pk[j] = (j < nm) ? 1.0 / nm : 0.0;
+    ps->pkllim = 1.0 / 10.0;
+    ps->nreinit = 1;
+  }
+}
+__global__ void rj_pk_population_kernel(RjPkShared *ps, const unsigned long long *visits, const double *gam, int m, int nm,
+                                        int adapt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long dv[AMX_MAX_MODELS], tot = 0;
+  for (int j = 0; j < nm; j++) {
+    dv[j] = visits[j] - ps->prev[j];
+    ps->prev[j] = visits[j];
+    tot += dv[j];
+  }
+  if (!adapt || tot == 0ull) return;
+  double keep = 1.0;
+  for (int s = 0; s < m; s++) keep *= (1.0 - gam[s]);
+  const double G = 1.0 - keep;
+  bool low = false;
+  for (int j = 0; j < nm; j++) {
+    const double f = (double)dv[j] / (double)tot;
+    ps->pk[j] += G * (f - ps->pk[j]);
+    low |= (ps->pk[j] < ps->pkllim);
+  }
+  if (low) {
+    ps->nreinit++;
+    ps->pkllim = 1.0 / (10.0 * ps->nreinit);
+    for (int j = 0; j < nm; j++) ps->pk[j] = 1.0 / nm;
+  }
+}
+
 // stage [prop blob | target blob] into shared memory (8-byte words), or bind to global
 __device__ __forceinline__ void stage_blobs(const RjLaunch &a, double *smem, bool staged, const void *&pb,
                                             const void *&tb) {
@@ -45,7 +97,7 @@ __device__ __forceinline__ void stage_blobs(const RjLaunch &a, double *smem, boo
 }
 
 template <class CFG>
-__device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, long id) {
+__device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, long id, const double *pk_shared = nullptr) {
   c.k = s.k[id];
   c.lp = s.lp[id];
   c.pkllim = s.pkllim[id];
@@ -55,7 +107,8 @@ __device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, 
 #pragma unroll
   for (int i = 0; i < CFG::DMAX; i++) c.thn[i] = c.th[i];
 #pragma unroll
-  for (int j = 0; j < CFG::NMAX; j++) c.pk[j] = (j < s.nmodels) ? s.pk[(long)j * s.C + id] : 0.0;
+  for (int j = 0; j < CFG::NMAX; j++)
+    c.pk[j] = (j < s.nmodels) ? (pk_shared ? pk_shared[j] : s.pk[(long)j * s.C + id]) : 0.0;
   c.acc_b = c.try_b = c.acc_s = c.try_s = c.acc_j = c.try_j = 0;
   c.flops = 0;
   c.kn = 0;
@@ -148,7 +201,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   const long id = active ? gid : a.st.C - 1;  // tail lanes shadow the last chain, never write
 
   ChainRegs<CFG> c;
-  load_chain(c, a.st, id);
+  load_chain(c, a.st, id, a.pk_shared);
   RNG u;
   const unsigned long long draws0 = a.st.draws[id];
   open_stream(u, a, id, draws0);
@@ -213,7 +266,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
       if (lane == 0) s_hist[warp][m] += __popc(b);
     }
     if (traced) {
-      const long row = (long)gid * a.nsweeps + s;
+      const long row = (long)gid * a.tr_stride + a.tr_off + s;
       a.tr_k[row] = c.k;
       a.tr_lp[row] = c.lp;
       const int dk = P.h->dims[c.k];
@@ -246,6 +299,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
     unsigned long long t = 0;
     for (int w = 0; w < kRjWarps; w++) t += s_hist[w][threadIdx.x];
     atomicAdd(&a.visits[threadIdx.x], t);
+    atomicAdd(&a.visits_grp[(blockIdx.x % kRjGroups) * AMX_MAX_MODELS + threadIdx.x], t);
   }
   if (threadIdx.x == 0 && s_status) atomicOr(a.status, s_status);
 }
@@ -286,7 +340,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
   const long id = active ? gid : a.st.C - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   ChainRegs<CFG> c;
-  load_chain(c, a.st, id);
+  load_chain(c, a.st, id, a.pk_shared);
   const int dmax = a.st.dmax;
   for (int i = 0; i < dmax; i++) c.thn[i] = sp.thn[id * dmax + i];
   c.kn = sp.kn[id];
@@ -335,7 +389,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
       if (lane == 0) s_hist[warp][m] += __popc(b);
     }
     if (active && gid < a.ntrace) {
-      const long row = (long)gid * a.nsweeps + s;
+      const long row = (long)gid * a.tr_stride + a.tr_off + s;
       a.tr_k[row] = c.k;
       a.tr_lp[row] = c.lp;
       const int dk = P.h->dims[c.k];
@@ -367,6 +421,7 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
     unsigned long long t = 0;
     for (int w = 0; w < kRjWarps; w++) t += s_hist[w][threadIdx.x];
     atomicAdd(&a.visits[threadIdx.x], t);
+    atomicAdd(&a.visits_grp[(blockIdx.x % kRjGroups) * AMX_MAX_MODELS + threadIdx.x], t);
   }
   if (status && active) atomicOr(a.status, status);
 }
@@ -482,10 +537,13 @@ struct amx_rj {
   double *init_dev;
   double *tape_dev;
   unsigned long long tape_stride;
-  unsigned long long *visits_dev, *cnt_dev;
+  unsigned long long *visits_dev, *cnt_dev, *grp_dev;
+  unsigned long long grp_host[AMX_RJ_GROUPS * AMX_MAX_MODELS];  // group counts as of the last amx_rj_collect
   int *status_dev;
   double *gam_dev;
   long gam_cap;
+  int pk_mode, pk_seg;      // AMX_PK_PER_CHAIN / AMX_PK_POPULATION; sweeps per population update
+  RjPkShared *pk_shared;    // device
   int *tr_k;
   double *tr_lp, *tr_theta, *tr_pk;
   long tr_cap, last_nsweeps;
@@ -576,6 +634,7 @@ static RjLaunch base_launch(const amx_rj *rj) {
   a.tape = rj->tape_dev;
   a.tape_stride = rj->tape_stride;
   a.visits = rj->visits_dev;
+  a.visits_grp = rj->grp_dev;
   a.cnt = rj->cnt_dev;
   a.status = rj->status_dev;
   return a;
@@ -715,10 +774,17 @@ amx_rj *amx_rj_create(const amx_proposal *p, const amx_target *t, long nchains, 
   AMX_CUDA_PTR(cudaMemcpyAsync(rj->init_dev, init_flat, sizeof(double) * total_d, cudaMemcpyHostToDevice, stream()));
   AMX_CUDA_PTR(cudaMalloc(&rj->visits_dev, sizeof(unsigned long long) * AMX_MAX_MODELS));
   AMX_CUDA_PTR(cudaMalloc(&rj->cnt_dev, sizeof(unsigned long long) * 8));
+  AMX_CUDA_PTR(cudaMalloc(&rj->grp_dev, sizeof(rj->grp_host)));
+  AMX_CUDA_PTR(cudaMemsetAsync(rj->grp_dev, 0, sizeof(rj->grp_host), stream()));
   AMX_CUDA_PTR(cudaMalloc(&rj->status_dev, sizeof(int)));
   AMX_CUDA_PTR(cudaMemsetAsync(rj->visits_dev, 0, sizeof(unsigned long long) * AMX_MAX_MODELS, stream()));
   AMX_CUDA_PTR(cudaMemsetAsync(rj->cnt_dev, 0, sizeof(unsigned long long) * 8, stream()));
   AMX_CUDA_PTR(cudaMemsetAsync(rj->status_dev, 0, sizeof(int), stream()));
+  AMX_CUDA_PTR(cudaMalloc(&rj->pk_shared, sizeof(RjPkShared)));
+  AMX_CUDA_PTR(cudaMemsetAsync(rj->pk_shared, 0, sizeof(RjPkShared), stream()));
+  rj_pk_reset_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->nm);
+  rj->pk_mode = AMX_PK_PER_CHAIN;
+  rj->pk_seg = 25;
   AMX_CUDA_PTR(cudaEventCreate(&rj->e0));
   AMX_CUDA_PTR(cudaEventCreate(&rj->e1));
   rj->pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
@@ -731,7 +797,7 @@ void amx_rj_destroy(amx_rj *rj) {
   RjState &s = rj->st;
   cudaFree(s.theta); cudaFree(s.pk); cudaFree(s.lp); cudaFree(s.pkllim); cudaFree(s.k);
   cudaFree(s.nreinit); cudaFree(s.draws); cudaFree(rj->init_dev); cudaFree(rj->tape_dev);
-  cudaFree(rj->visits_dev); cudaFree(rj->cnt_dev); cudaFree(rj->status_dev); cudaFree(rj->gam_dev);
+  cudaFree(rj->visits_dev); cudaFree(rj->cnt_dev); cudaFree(rj->status_dev); cudaFree(rj->gam_dev); cudaFree(rj->pk_shared); cudaFree(rj->grp_dev);
   cudaFree(rj->tr_k); cudaFree(rj->tr_lp); cudaFree(rj->tr_theta); cudaFree(rj->tr_pk);
   cudaEventDestroy(rj->e0);
   cudaEventDestroy(rj->e1);
@@ -786,6 +852,26 @@ int amx_rj_set_modes(amx_rj *rj, int student_t_dof, int do_perm) {
   return AMX_OK;
 }
 
+int amx_rj_set_pk_mode(amx_rj *rj, int mode, int segment_sweeps) {
+  if (!rj || (mode != AMX_PK_PER_CHAIN && mode != AMX_PK_POPULATION) || segment_sweeps < 0)
+    return fail(AMX_EINVAL, "amx_rj_set_pk_mode: bad arguments");
+  rj->pk_mode = mode;
+  if (segment_sweeps > 0) rj->pk_seg = segment_sweeps;
+  return AMX_OK;
+}
+
+int amx_rj_get_pk_shared(const amx_rj *rj, double *pk, int *nreinit, double *pkllim) {
+  if (!rj) return fail(AMX_EINVAL, "null handle");
+  RjPkShared h;
+  AMX_CUDA(cudaMemcpyAsync(&h, rj->pk_shared, sizeof(h), cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
+  if (pk)
+    for (int j = 0; j < rj->nm; j++) pk[j] = h.pk[j];
+  if (nreinit) *nreinit = h.nreinit;
+  if (pkllim) *pkllim = h.pkllim;
+  return AMX_OK;
+}
+
 int amx_rj_set_chain_base(amx_rj *rj, uint64_t first_chain_id) {
   if (!rj) return fail(AMX_EINVAL, "null handle");
   rj->chain_base = first_chain_id;
@@ -809,6 +895,8 @@ int amx_rj_set_tape(amx_rj *rj, const double *tape, long stride) {
 
 int amx_rj_init_chains(amx_rj *rj) {
   if (!rj) return fail(AMX_EINVAL, "null handle");
+  rj_pk_reset_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->nm);  // pk = 1/nmodels, nreinit = 1, pkllim = 0.1 (:441-446)
+  count_launch();
   RjLaunch a = base_launch(rj);
   const unsigned grid = (unsigned)((rj->C + kRjThreads - 1) / kRjThreads);
   const bool tape = rj->tape_dev != nullptr;
@@ -911,11 +999,15 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
   if (nsweeps > rj->gam_cap) {
     cudaFree(rj->gam_dev);
     rj->gam_dev = nullptr;
+    rj->gam_cap = 0;
     AMX_CUDA(cudaMalloc(&rj->gam_dev, sizeof(double) * nsweeps));
     rj->gam_cap = nsweeps;
   }
   if (rj->ntrace > 0 && nsweeps * rj->ntrace > rj->tr_cap) {
     cudaFree(rj->tr_k); cudaFree(rj->tr_lp); cudaFree(rj->tr_theta); cudaFree(rj->tr_pk);
+    rj->tr_k = nullptr;
+    rj->tr_lp = rj->tr_theta = rj->tr_pk = nullptr;
+    rj->tr_cap = 0;
     const size_t rows = (size_t)nsweeps * rj->ntrace;
     AMX_CUDA(cudaMalloc(&rj->tr_k, sizeof(int) * rows));
     AMX_CUDA(cudaMalloc(&rj->tr_lp, sizeof(double) * rows));
@@ -924,25 +1016,44 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
     rj->tr_cap = (long)rows;
   }
   RjLaunch a = base_launch(rj);
-  a.gam = rj->gam_dev;
-  a.sweep0 = rj->sweep_i;
-  a.nsweeps = (int)nsweeps;
-  a.adapt = (do_adapt && !burning) ? 1 : 0;
+  const int adapt = (do_adapt && !burning) ? 1 : 0;
+  const bool pop = rj->pk_mode == AMX_PK_POPULATION;
   a.ntrace = rj->ntrace;
+  a.tr_stride = nsweeps;
   a.tr_k = rj->tr_k;
   a.tr_lp = rj->tr_lp;
   a.tr_theta = rj->tr_theta;
   a.tr_pk = rj->tr_pk;
+  a.pk_shared = pop ? rj->pk_shared->pk : nullptr;
+  a.adapt = pop ? 0 : adapt;  // population mode: the shared pk moves between segments, not inside the sweep
   cudaEvent_t e0, e1;
   AMX_CUDA(cudaEventCreate(&e0));
   AMX_CUDA(cudaEventCreate(&e1));
   rj_gamma_kernel<<<(unsigned)((nsweeps + 255) / 256), 256, 0, stream()>>>(rj->gam_dev, rj->sweep_i, (int)nsweeps);
   count_launch();
   AMX_CUDA(cudaEventRecord(e0, stream()));
-  int rc;
-  if (is_host_target(rj)) rc = split_sweeps(rj, a);
-  else rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
-  if (rc) return rc;
+  // Population pk mode while adapting: segments of pk_seg sweeps, each followed by the shared update.  Otherwise
+  // (per-chain mode, or nothing to adapt) the whole call is one launch.
+  const long seg = (pop && adapt) ? (long)rj->pk_seg : nsweeps;
+  int rc = AMX_OK;
+  for (long off = 0; off < nsweeps && rc == AMX_OK; off += seg) {
+    const long m = (nsweeps - off < seg) ? nsweeps - off : seg;
+    a.gam = rj->gam_dev + off;
+    a.sweep0 = rj->sweep_i + (unsigned long long)off;
+    a.nsweeps = (int)m;
+    a.tr_off = off;
+    if (is_host_target(rj)) rc = split_sweeps(rj, a);
+    else rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
+    if (rc == AMX_OK && pop) {  // also while burning: the histogram baseline must follow the visits
+      rj_pk_population_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->visits_dev, a.gam, (int)m, rj->nm, adapt);
+      count_launch();
+    }
+  }
+  if (rc) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+  }
   AMX_CUDA(cudaEventRecord(e1, stream()));
   rj->pending->push_back({e0, e1});
   rj->sweep_i += (unsigned long long)nsweeps;
@@ -963,22 +1074,55 @@ int amx_rj_collect(amx_rj *rj, unsigned long long *visits, amx_rj_stats *st, int
   rj->pending->clear();
   unsigned long long cnt[8];
   int status = 0;
-  AMX_CUDA(cudaMemcpy(cnt, rj->cnt_dev, sizeof(cnt), cudaMemcpyDeviceToHost));
-  AMX_CUDA(cudaMemcpy(&status, rj->status_dev, sizeof(int), cudaMemcpyDeviceToHost));
-  if (visits) AMX_CUDA(cudaMemcpy(visits, rj->visits_dev, sizeof(unsigned long long) * rj->nm, cudaMemcpyDeviceToHost));
+  AMX_CUDA(cudaMemcpyAsync(cnt, rj->cnt_dev, sizeof(cnt), cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaMemcpyAsync(&status, rj->status_dev, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  if (visits)
+    AMX_CUDA(cudaMemcpyAsync(visits, rj->visits_dev, sizeof(unsigned long long) * rj->nm, cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaMemcpyAsync(rj->grp_host, rj->grp_dev, sizeof(rj->grp_host), cudaMemcpyDeviceToHost, stream()));
+  AMX_CUDA(cudaStreamSynchronize(stream()));
   if (st) {
     st->acc_block = cnt[0]; st->try_block = cnt[1]; st->acc_single = cnt[2]; st->try_single = cnt[3];
     st->acc_jump = cnt[4]; st->try_jump = cnt[5]; st->flops = cnt[6]; st->draws = cnt[7];
     st->kernel_ms = rj->kernel_ms;
   }
-  if (reset) {
-    AMX_CUDA(cudaMemset(rj->visits_dev, 0, sizeof(unsigned long long) * AMX_MAX_MODELS));
-    AMX_CUDA(cudaMemset(rj->cnt_dev, 0, sizeof(unsigned long long) * 8));
-    AMX_CUDA(cudaMemset(rj->status_dev, 0, sizeof(int)));
+  if (reset) {  // on the library stream: the next sweep kernel's atomics are ordered after these
+    AMX_CUDA(cudaMemsetAsync(rj->visits_dev, 0, sizeof(unsigned long long) * AMX_MAX_MODELS, stream()));
+    AMX_CUDA(cudaMemsetAsync(rj->pk_shared->prev, 0, sizeof(unsigned long long) * AMX_MAX_MODELS, stream()));
+    AMX_CUDA(cudaMemsetAsync(rj->cnt_dev, 0, sizeof(unsigned long long) * 8, stream()));
+    AMX_CUDA(cudaMemsetAsync(rj->grp_dev, 0, sizeof(rj->grp_host), stream()));
+    AMX_CUDA(cudaMemsetAsync(rj->status_dev, 0, sizeof(int), stream()));
     rj->kernel_ms = 0.0;
   }
   if (status & 1) return fail(AMX_ETAPE, "injected uniform tape exhausted");
   if (status & 2) return fail(AMX_ENUMERIC, "a chain reached a NaN log-posterior");
+  return AMX_OK;
+}
+
+int amx_rj_visit_se(const amx_rj *rj, double *p, double *se, int *ngroups) {
+  if (!rj) return fail(AMX_EINVAL, "null handle");
+  const int nm = rj->nm;
+  double tot = 0.0, gt[AMX_RJ_GROUPS];
+  int G = 0;
+  for (int g = 0; g < AMX_RJ_GROUPS; g++) {
+    gt[g] = 0.0;
+    for (int k = 0; k < nm; k++) gt[g] += (double)rj->grp_host[g * AMX_MAX_MODELS + k];
+    tot += gt[g];
+    if (gt[g] > 0.0) G++;
+  }
+  if (ngroups) *ngroups = G;
+  for (int k = 0; k < nm; k++) {
+    double vk = 0.0;
+    for (int g = 0; g < AMX_RJ_GROUPS; g++) vk += (double)rj->grp_host[g * AMX_MAX_MODELS + k];
+    const double pk = tot > 0.0 ? vk / tot : 0.0;
+    double v = 0.0;
+    for (int g = 0; g < AMX_RJ_GROUPS; g++)
+      if (gt[g] > 0.0) {
+        const double w = gt[g] / tot, dg = (double)rj->grp_host[g * AMX_MAX_MODELS + k] / gt[g] - pk;
+        v += w * w * dg * dg;
+      }
+    if (p) p[k] = pk;
+    if (se) se[k] = G > 1 ? sqrt(v * (double)G / (double)(G - 1)) : 0.0 / 0.0;
+  }
   return AMX_OK;
 }
 

@@ -25,6 +25,7 @@ using RjCfgG = RjCfg<AMX_MAX_DIM, AMX_MAX_COMPS, AMX_MAX_MODELS>;  // general (l
 
 constexpr double kHalfLog2Pi = 0.9189385332046727;  // literal at automix.c:1052
 constexpr int kRjThreads = 128;
+constexpr int kRjGroups = AMX_RJ_GROUPS;  // disjoint groups of chains whose visit counts are kept apart (Monte-Carlo error)
 constexpr int kRjWarps = kRjThreads / 32;
 
 // A per-thread scratch vector kept in shared memory, laid out [element][thread] (conflict-free): a run-time
@@ -405,6 +406,7 @@ struct RjLaunch {
   unsigned long long chain_base;  // global id of chain 0 of this population
   const double *tape;          // parity mode
   unsigned long long tape_stride;
+  const double *pk_shared;     // population pk mode: [nmodels] jump probabilities shared by every chain (else NULL)
   const double *gam;           // [nsweeps] pk-adaptation step sizes (sweep_i+1)^(-2/3)
   unsigned long long sweep0;   // sweep_i of the first sweep of this launch
   int nsweeps;
@@ -412,10 +414,12 @@ struct RjLaunch {
   RjModes modes;
   // outputs
   unsigned long long *visits;  // [nmodels]
+  unsigned long long *visits_grp;  // [kRjGroups][AMX_MAX_MODELS] the same counts by group of chains (CTA index mod kRjGroups)
   unsigned long long *cnt;     // [8]: 6 runStats counters, flops, draws
   int *status;                 // bit 0: tape overrun, bit 1: NaN log-posterior
   // trace chains
   int ntrace;
+  long tr_stride, tr_off;      // trace row of (chain, sweep s of this launch) = chain * tr_stride + tr_off + s
   int *tr_k;
   double *tr_lp, *tr_theta, *tr_pk;
 };

@@ -36,6 +36,7 @@ typedef struct sampler_ext {
   long rj_chains, rwm_chains;
   uint64_t seed;
   int seed_set;
+  int pk_mode; /* -1: default (population when more than one chain) */
   int st_alloc_nsweep; /* runStats arrays we own */
   amx_sampler_stats stats;
   struct sampler_ext *next;
@@ -49,6 +50,7 @@ static sampler_ext *ext_of(const amSampler *am, int create) {
   if (!create) return NULL;
   sampler_ext *e = (sampler_ext *)calloc(1, sizeof(*e));
   e->am = am;
+  e->pk_mode = -1;
   e->next = g_ext;
   g_ext = e;
   return e;
@@ -495,6 +497,8 @@ static int ensure_population(amSampler *am, sampler_ext *e, int n_trace) {
       e->rj = amx_rj_create(e->prop, tgt, C, init, seed ^ 0x9E3779B97F4A7C15ull, n_trace);
       if (e->rj) {
         e->stats.nchains = C;
+        const int mode = e->pk_mode >= 0 ? e->pk_mode : (C > 1 ? AMX_PK_POPULATION : AMX_PK_PER_CHAIN);
+        amx_rj_set_pk_mode(e->rj, mode, 0);
         rc = amx_rj_init_chains(e->rj); /* initChain (reference :423-449) for every chain */
       }
     }
@@ -540,6 +544,7 @@ static void collect_population(sampler_ext *e, int nm) {
   int rc = amx_rj_collect(e->rj, vis, &rs, 1);
   report(e, "amx_rj_collect", rc);
   for (int k = 0; k < nm && k < 32; k++) e->stats.visits[k] = vis[k];
+  amx_rj_visit_se(e->rj, NULL, e->stats.visit_se, NULL);
   e->stats.acc_block = rs.acc_block;
   e->stats.try_block = rs.try_block;
   e->stats.acc_single = rs.acc_single;
@@ -663,6 +668,13 @@ int amx_sampler_set_chains(amSampler *am, long rj_chains, long rwm_chains) {
   sampler_ext *e = ext_of(am, 1);
   e->rj_chains = rj_chains;
   e->rwm_chains = rwm_chains;
+  return AMX_OK;
+}
+int amx_sampler_set_pk_mode(amSampler *am, int mode) {
+  sampler_ext *e = ext_of(am, 1);
+  if (mode != AMX_PK_PER_CHAIN && mode != AMX_PK_POPULATION) return AMX_EINVAL;
+  e->pk_mode = mode;
+  if (e->rj) amx_rj_set_pk_mode(e->rj, mode, 0);
   return AMX_OK;
 }
 int amx_sampler_set_seed(amSampler *am, uint64_t seed) {

@@ -154,6 +154,21 @@ int amx_rj_set_chain_base(amx_rj *rj, uint64_t first_chain_id);
  * innovations with their variable-length gamma rejection draws, and random permutation of the standardised
  * vector.  Defaults 0 / 0. */
 int amx_rj_set_modes(amx_rj *rj, int student_t_dof, int do_perm);
+/* How the adaptive model-jump probabilities pk (automix.c:1258-1282) are kept.
+ *   AMX_PK_PER_CHAIN   every chain adapts its own pk after every sweep: the reference's rule, bit for bit per chain
+ *                      (the parity mode).  As an estimator over many SHORT chains it carries the reference's own
+ *                      finite-time adaptation bias (a chain's pk is correlated with its recent path).
+ *   AMX_PK_POPULATION  one pk shared by all chains, moved between segments of `segment_sweeps` sweeps by the
+ *                      reference's update with the population's model-visit fractions (the warp-aggregated
+ *                      histogram of the sweep kernel) in place of the chain's indicator, then the reference's
+ *                      re-initialisation rule.  Within a segment every sweep leaves the posterior invariant, so
+ *                      population estimates are unbiased; judged by posterior model probabilities, not per step.
+ * segment_sweeps = 0 keeps the current value (default 25). */
+#define AMX_PK_PER_CHAIN 0
+#define AMX_PK_POPULATION 1
+int amx_rj_set_pk_mode(amx_rj *rj, int mode, int segment_sweeps);
+/* The shared pk of the population mode (pk[nmodels]) and its re-initialisation state; any may be NULL. */
+int amx_rj_get_pk_shared(const amx_rj *rj, double *pk, int *nreinit, double *pkllim);
 /* Parity mode: chain c draws tape[c*stride + i] instead of its Philox stream. */
 int amx_rj_set_tape(amx_rj *rj, const double *tape, long stride);
 /* Start every chain as initChain does (one uniform picks the model). */
@@ -175,6 +190,13 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt);
  * all chains and all sweeps since the last reset) and the counters. */
 int amx_rj_collect(amx_rj *rj, unsigned long long *visits, amx_rj_stats *st,
                    int reset);
+/* Monte-Carlo error of the model-visit fractions.  The sweep kernels keep the visit counts of AMX_RJ_GROUPS disjoint
+ * groups of chains apart (chains are independent, so group means are); after amx_rj_collect this returns for each
+ * model the visit fraction p[k] over the counts collected and its standard error se[k] from the spread of the
+ * group fractions (NaN with fewer than two non-empty groups: populations below 256 chains), and the number of
+ * non-empty groups.  Any output may be NULL. */
+#define AMX_RJ_GROUPS 64
+int amx_rj_visit_se(const amx_rj *rj, double *p, double *se, int *ngroups);
 /* Per-sweep records of the trace chains for the last amx_rj_sweeps call:
  * k[n_trace*nsweeps], lp[...], theta[n_trace*nsweeps*dmax], pk[...*nmodels]. */
 int amx_rj_get_trace(const amx_rj *rj, int *k, double *lp, double *theta,

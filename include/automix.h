@@ -184,6 +184,8 @@ typedef struct amx_sampler_stats {
   unsigned long long acc_block, try_block, acc_single, try_single, acc_jump, try_jump;
   double kernel_ms_rwm, kernel_ms_em, kernel_ms_rj;
   int last_error;                           /* AMX_OK or the code of the last failure */
+  double visit_se[32];                      /* Monte-Carlo standard error of visits[k] / sum(visits), from the spread
+                                               between disjoint groups of chains (NaN below 256 chains) */
 } amx_sampler_stats;
 
 /* Use a __device__ plug-in (amx_target_gaussmix / _quad / _coalmine) instead of the scalar
@@ -198,6 +200,12 @@ int amx_sampler_set_chains(amSampler *am, long rj_chains, long rwm_chains);
  * from the clock as the reference does).  Also reseeds the library's sdrand() stream, which draws
  * the start rows of the mixture fit, so a seeded run is reproducible end to end. */
 int amx_sampler_set_seed(amSampler *am, uint64_t seed);
+/* How the adaptive jump probabilities pk are kept by a population (include/amx.h, amx_rj_set_pk_mode):
+ * 0 = per chain, the reference's rule for its one chain; 1 = one pk shared by the population, adapted from the
+ * population's model-visit histogram.  Default: 1 when the population has more than one chain (many short chains
+ * that each adapt their own pk inherit the reference's finite-time adaptation bias; the shared rule has none),
+ * 0 for a single chain (then the run is the reference's chain). */
+int amx_sampler_set_pk_mode(amSampler *am, int mode);
 const amx_sampler_stats *amx_sampler_stats_get(const amSampler *am);
 /* Per-model posterior moments over the population after rjmcmc_samples: one draw per chain (its final
  * state); count = chains in that model, mean[d], unbiased cov[d*d], mean log-posterior (any may be NULL).
