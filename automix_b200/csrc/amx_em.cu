@@ -1376,6 +1376,8 @@ __global__ void __launch_bounds__(256) autorj_generic_kernel(int d, long n, cons
   }
 }
 
+#include "amx_em2.cuh"
+
 }  // namespace amx
 
 using namespace amx;
@@ -1415,6 +1417,61 @@ static int em_launch_d(int d, EmArgs &a, unsigned grid, size_t smem, cudaStream_
   if (d <= 12) return em_launch_one<12>(a, grid, smem, st);
   if (d <= 20) return em_launch_one<20>(a, grid, smem, st);
   return em_launch_one<32>(a, grid, smem, st);
+}
+
+
+// ---- second-generation kernel (amx_em2.cuh): d <= 12, one persistent CTA per SM ---------------------------------
+struct V2Plan {
+  int nteam, ns;
+  size_t smem;
+  int region0_doubles;
+};
+template <int DMAX, int NTEAM>
+static int em2_plan_one(int d, int Lmax, size_t max_dyn, V2Plan *p) {
+  const size_t fixed = v2_fixed_doubles<DMAX>(d, Lmax), scratch = v2_scratch_doubles<DMAX, NTEAM>();
+  const size_t stage = (size_t)(d + Lmax + 1) * kV2TS;
+  const size_t avail = max_dyn / sizeof(double);
+  if (avail < fixed + scratch + 2 * stage) return fail(AMX_ECUDA, "EM kernel does not fit in shared memory (d=%d, Lmax=%d)", d, Lmax);
+  int ns = (int)((avail - fixed) / stage);
+  if (ns > 8) ns = 8;
+  if (ns < 2) return fail(AMX_ECUDA, "EM kernel: fewer than two ring stages fit (d=%d, Lmax=%d)", d, Lmax);
+  size_t region0 = (size_t)ns * stage;
+  if (region0 < scratch) region0 = scratch;
+  p->nteam = NTEAM;
+  p->ns = ns;
+  p->region0_doubles = (int)region0;
+  p->smem = sizeof(double) * (region0 + fixed);
+  AMX_CUDA(cudaFuncSetAttribute(em_fit_v2_kernel<DMAX, NTEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  return AMX_OK;
+}
+template <int DMAX, int NTEAM>
+static int em2_launch_one(EmArgs &a, V2Args &v, unsigned grid, size_t smem, cudaStream_t st) {
+  void *args[] = {&a, &v};
+  AMX_CUDA(cudaLaunchCooperativeKernel((void *)em_fit_v2_kernel<DMAX, NTEAM>, dim3(grid), dim3(NTEAM * 128), args, smem, st));
+  count_launch();
+  return AMX_OK;
+}
+#define AMX_V2_DISPATCH(FN, ...)                                              \
+  do {                                                                        \
+    if (nteam == 2) {                                                         \
+      if (d <= 4) return FN<4, 2>(__VA_ARGS__);                               \
+      if (d <= 8) return FN<8, 2>(__VA_ARGS__);                               \
+      if (d <= 10) return FN<10, 2>(__VA_ARGS__);                             \
+      return FN<12, 2>(__VA_ARGS__);                                          \
+    }                                                                         \
+    if (d <= 4) return FN<4, 3>(__VA_ARGS__);                                 \
+    if (d <= 8) return FN<8, 3>(__VA_ARGS__);                                 \
+    if (d <= 10) return FN<10, 3>(__VA_ARGS__);                               \
+    return FN<12, 3>(__VA_ARGS__);                                            \
+  } while (0)
+static int em2_plan(int d, int nteam, int Lmax, size_t max_dyn, V2Plan *p) { AMX_V2_DISPATCH(em2_plan_one, d, Lmax, max_dyn, p); }
+static int em2_launch(int d, int nteam, EmArgs &a, V2Args &v, unsigned grid, size_t smem, cudaStream_t st) {
+  AMX_V2_DISPATCH(em2_launch_one, a, v, grid, smem, st);
+}
+
+__global__ void em_gather_rows_kernel(const double *x, const int *idx, int L, int d, double *out) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < L * d; q += gridDim.x * blockDim.x)
+    out[q] = x[(size_t)idx[q / d] * d + (q % d)];
 }
 
 // One fit over ndev GPUs (ndev = 1: the ordinary fit).  The samples are split into contiguous shards, one
@@ -1522,6 +1579,28 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   const int nbuf = (use_tma && nb && atoi(nb) == 2) ? 2 : 1;
   const char *fu = getenv("AMX_EM_FUSED");
   const int fused = (d <= 12 && use_tma && nbuf == 1) ? (fu ? (atoi(fu) != 0) : 1) : 0;  // entries e, e+64 cover tri(12) = 78
+  // second-generation kernel (amx_em2.cuh) wherever the fused step applies; AMX_EM_V2=0 keeps the first generation
+  const char *v2e = getenv("AMX_EM_V2"), *v2t = getenv("AMX_EM_TEAMS");
+  const bool use_v2 = fused && d <= kV2Dmax && (v2e ? atoi(v2e) != 0 : true);
+  const int nteam = (v2t && atoi(v2t) == 2) ? 2 : 3;
+  V2Plan plan;
+  memset(&plan, 0, sizeof(plan));
+  if (use_v2) {
+    int max_dyn = 0;
+    AMX_CUDA(cudaDeviceGetAttribute(&max_dyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, devs[0]));
+    for (int g = 0; g < ndev; g++) {  // the attribute is per device
+      AMX_CUDA(cudaSetDevice(devs[g]));
+      if (int prc = em2_plan(d, nteam, Lmax, (size_t)max_dyn - 256, &plan)) {
+        cudaSetDevice(home);
+        return prc;
+      }
+    }
+    if (const char *nse = getenv("AMX_EM_STAGES")) {
+      const int want_ns = atoi(nse);
+      if (want_ns >= 2 && want_ns < plan.ns) plan.ns = want_ns;
+    }
+    AMX_CUDA(cudaSetDevice(home));
+  }
   size_t smem = nbuf * sizeof(double) * (size_t)(d + Lmax + 1 + (fused ? d : 0)) * kEmTS;
   {  // room for the reduction scratch and the leader's state, which alias the tile (see em_fit_kernel)
     const size_t need = d <= 4 ? em_scratch_bytes<4>() : d <= 8 ? em_scratch_bytes<8>() : d <= 12 ? em_scratch_bytes<12>()
@@ -1530,6 +1609,10 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   }
 
   EmArgs A[kEmMaxDev];
+  V2Args V[kEmMaxDev];
+  V2Sync *v2sync[kEmMaxDev];
+  memset(V, 0, sizeof(V));
+  memset(v2sync, 0, sizeof(v2sync));
   cudaStream_t st[kEmMaxDev];
   int *idx_dev = nullptr;
   double *init_rows = nullptr;
@@ -1563,22 +1646,34 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
         }
     }
 
+  // one stream per GPU: everything a kernel reads is enqueued on the stream that launches it (never on the legacy
+  // default stream, which nothing orders against non-blocking streams)
+  for (int g = 0; g < ndev; g++) {
+    AMX_CUDA(cudaSetDevice(devs[g]));
+    if (g == 0 && ndev == 1) st[g] = stream();
+    else AMX_CUDA(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
+  }
   // GPU 0: the control block, the traces and the start rows
   AMX_CUDA(cudaSetDevice(devs[0]));
   AMX_CUDA(ws_malloc(&ctrl, sizeof(EmCtrl)));
-  AMX_CUDA(cudaMemset(ctrl, 0, sizeof(EmCtrl)));
+  AMX_CUDA(cudaMemsetAsync(ctrl, 0, sizeof(EmCtrl), st[0]));
   AMX_CUDA(ws_malloc(&init_rows, sizeof(double) * (size_t)Lmax * d));
   AMX_CUDA(ws_malloc(&tr_L, sizeof(int) * cap));
   AMX_CUDA(ws_malloc(&tr_ann, sizeof(int) * cap));
   AMX_CUDA(ws_malloc(&tr_ll, sizeof(double) * cap));
   AMX_CUDA(ws_malloc(&tr_cost, sizeof(double) * cap));
-  for (int l = 0; l < Lmax; l++) {
-    if (x_host)
-      AMX_CUDA(cudaMemcpy(init_rows + (size_t)l * d, x_host + (size_t)init_idx[l] * d, sizeof(double) * d, cudaMemcpyHostToDevice));
-    else
-      AMX_CUDA(cudaMemcpy(init_rows + (size_t)l * d, x_dev0 + (size_t)init_idx[l] * d, sizeof(double) * d, cudaMemcpyDeviceToDevice));
+  if (x_host) {  // the Lmax start rows, gathered on the host: one small copy
+    std::vector<double> rows_h((size_t)Lmax * d);
+    for (int l = 0; l < Lmax; l++) memcpy(&rows_h[(size_t)l * d], x_host + (size_t)init_idx[l] * d, sizeof(double) * d);
+    AMX_CUDA(cudaMemcpyAsync(init_rows, rows_h.data(), sizeof(double) * rows_h.size(), cudaMemcpyHostToDevice, st[0]));
+    AMX_CUDA(cudaStreamSynchronize(st[0]));  // rows_h leaves scope
+  } else {       // samples already on the device: gather with a kernel, ordered after whatever filled them on this stream
+    AMX_CUDA(ws_malloc(&idx_dev, sizeof(int) * kEmLmax));
+    AMX_CUDA(cudaMemcpyAsync(idx_dev, init_idx, sizeof(int) * Lmax, cudaMemcpyHostToDevice, st[0]));
+    em_gather_rows_kernel<<<1, 256, 0, st[0]>>>(x_dev0, idx_dev, Lmax, d, init_rows);
+    count_launch();
+    AMX_CUDA(cudaGetLastError());
   }
-  (void)idx_dev;
 
   // per-GPU shards
   for (int g = 0; g < ndev; g++) {
@@ -1602,8 +1697,6 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     a.trace_ann = tr_ann;
     a.trace_loglik = tr_ll;
     a.trace_cost = tr_cost;
-    if (g == 0 && ndev == 1) st[g] = stream();
-    else AMX_CUDA(cudaStreamCreateWithFlags(&st[g], cudaStreamNonBlocking));
     if (x_host) {
       double *xs = nullptr;
       AMX_CUDA(ws_malloc(&xs, sizeof(double) * (size_t)a.n * d));
@@ -1615,15 +1708,27 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     AMX_CUDA(ws_malloc(&a.xT, sizeof(double) * (size_t)d * a.npad));
     AMX_CUDA(ws_malloc(&a.E, sizeof(double) * (size_t)Lmax * a.npad));
     AMX_CUDA(ws_malloc(&a.wnxt, sizeof(double) * (size_t)a.npad));
-    AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, st[g]));
-    AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, st[g]));
-    AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, st[g]));
+    if (!use_v2) {  // the second generation never reads a padding sample's cache, and has no w_next array
+      AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, st[g]));
+      AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, st[g]));
+      AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, st[g]));
+    } else if (a.npad > a.n) {  // the tail of the last tile is read by the bulk copies (and ignored): keep it finite
+      for (int j = 0; j < d; j++)
+        AMX_CUDA(cudaMemsetAsync(a.xT + (size_t)j * a.npad + a.n, 0, sizeof(double) * (size_t)(a.npad - a.n), st[g]));
+      for (int l = 0; l < Lmax; l++)
+        AMX_CUDA(cudaMemsetAsync(a.E + (size_t)l * a.npad + a.n, 0, sizeof(double) * (size_t)(a.npad - a.n), st[g]));
+    }
     if (cur_w) AMX_CUDA(ws_malloc(&a.w_out, sizeof(double) * (size_t)a.n * Lmax));
     int per_sm = 0;
-    if ((rc = em_occupancy_d(d, smem, &per_sm))) return rc;
+    if (use_v2) per_sm = 1;
+    else if ((rc = em_occupancy_d(d, smem, &per_sm))) return rc;
     if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM (%zu B of shared memory)", smem);
     long want = a.npad / kEmThreads, capb = (long)sms * per_sm;
     unsigned grid = (unsigned)(want < capb ? want : capb);
+    if (use_v2) {
+      AMX_CUDA(ws_malloc(&v2sync[g], sizeof(V2Sync)));
+      AMX_CUDA(cudaMemsetAsync(v2sync[g], 0, sizeof(V2Sync), st[g]));
+    }
     EmDev dv;
     memset(&dv, 0, sizeof(dv));
     dv.grid = (int)grid;
@@ -1636,7 +1741,13 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     AMX_CUDA(cudaMemsetAsync(dv.arrive, 0, sizeof(unsigned) * 8, st[g]));
     AMX_CUDA(cudaMemsetAsync(dv.pub, 0, sizeof(EmPublic), st[g]));
     for (int h = 0; h < ndev; h++) A[h].dev[g] = dv;
+    V[g].part = dv.part;
+    V[g].ns = plan.ns;
+    V[g].region0_doubles = plan.region0_doubles;
+    V[g].debug = getenv("AMX_EM_DEBUG") ? 1 : 0;
   }
+  for (int g = 0; g < ndev; g++)
+    for (int h = 0; h < ndev; h++) V[g].sync[h] = v2sync[h];
   for (int g = 0; g < ndev; g++) {  // everything above must have landed before any kernel starts
     AMX_CUDA(cudaSetDevice(devs[g]));
     AMX_CUDA(cudaStreamSynchronize(st[g]));
@@ -1651,7 +1762,8 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   int launched = 0;
   for (int g = 0; g < ndev && rc == AMX_OK; g++) {
     cudaSetDevice(devs[g]);
-    rc = em_launch_d(d, A[g], (unsigned)A[g].dev[g].grid, smem, st[g]);
+    rc = use_v2 ? em2_launch(d, nteam, A[g], V[g], (unsigned)A[g].dev[g].grid, plan.smem, st[g])
+                : em_launch_d(d, A[g], (unsigned)A[g].dev[g].grid, smem, st[g]);
     if (rc == AMX_OK) launched++;
   }
   if (rc != AMX_OK && launched > 0) {
@@ -1665,6 +1777,7 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
       cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
       cudaMemcpyAsync(A[g].dev[g].pub, &stop_pub, sizeof(stop_pub), cudaMemcpyHostToDevice, side);
       cudaMemsetAsync(A[g].dev[g].flags, 0xFF, sizeof(unsigned) * 8 * (size_t)A[g].dev[g].grid, side);
+      // (second generation: the partners' flags never rise; its watchdog ends the kernels that did start)
       cudaStreamSynchronize(side);
       cudaStreamDestroy(side);
     }
@@ -1719,7 +1832,10 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
       res->flops = c->flops;
       res->bytes = 8.0 * d * (double)n * (double)c->comp_steps;
     }
-    if (getenv("AMX_EM_DEBUG"))
+    if (getenv("AMX_EM_DEBUG") && use_v2)
+      fprintf(stderr, "[em2 dbg] %d GPU(s), %d teams, %d stages, %zu B smem; CTA 0 of GPU 0, cycles: data passes %lld | exchange %lld | sequential section %lld (%ld component steps)\n",
+              ndev, nteam, plan.ns, plan.smem, c->dbg[0], c->dbg[1], c->dbg[3], c->comp_steps);
+    else if (getenv("AMX_EM_DEBUG"))
       fprintf(stderr, "[em dbg] %d GPU(s), cycles on GPU 0: block0 data pass %lld | leader: arrive-skew+reduce %lld logic %lld | block0 wait %lld reload %lld (phases ~%ld) | scatter passes %lld refresh passes %lld\n",
               ndev, c->dbg[0], c->dbg[1], c->dbg[3], c->dbg[4], c->dbg[5], 2 * c->comp_steps, c->dbg[6], c->dbg[7]);
     status = c->status;
@@ -1730,9 +1846,11 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     if (x_host) ws_free(const_cast<double *>(a.x));
     ws_free(a.xT); ws_free(a.E); ws_free(a.wnxt); ws_free(a.w_out);
     ws_free(a.dev[g].part); ws_free(a.dev[g].devrow); ws_free(a.dev[g].flags); ws_free(a.dev[g].arrive); ws_free(a.dev[g].pub);
+    ws_free(v2sync[g]);
     if (!(g == 0 && ndev == 1)) cudaStreamDestroy(st[g]);
   }
   cudaSetDevice(devs[0]);
+  ws_free(idx_dev);
   ws_free(ctrl); ws_free(init_rows); ws_free(tr_L); ws_free(tr_ann); ws_free(tr_ll); ws_free(tr_cost);
   cudaSetDevice(home);
   if (rc != AMX_OK) return rc;
@@ -1779,11 +1897,12 @@ int amx_em_fit(int d, long n, const double *x, int Lmax, int maxit, const int *i
   if (int rc = require_device()) return rc;
   if (d < 1 || n < 1 || !x) return fail(AMX_EINVAL, "amx_em_fit: empty input");
   double *x_dev = nullptr;
-  AMX_CUDA(cudaMalloc(&x_dev, sizeof(double) * (size_t)n * d));
-  AMX_CUDA(cudaMemcpyAsync(x_dev, x, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, stream()));
-  int rc = em_fit_impl(d, n, x_dev, Lmax, maxit, init_idx, wt, mean, tri, trace_L, trace_loglik, trace_cost, trace_ann,
-                       cur_wt, cur_mean, cur_tri, cur_L, cur_w, res);
-  cudaFree(x_dev);
+  AMX_CUDA(ws_malloc(&x_dev, sizeof(double) * (size_t)n * d));  // from the workspace pool, like the rest of the fit
+  cudaError_t ce = cudaMemcpyAsync(x_dev, x, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, stream());
+  int rc = ce == cudaSuccess ? em_fit_impl(d, n, x_dev, Lmax, maxit, init_idx, wt, mean, tri, trace_L, trace_loglik, trace_cost,
+                                           trace_ann, cur_wt, cur_mean, cur_tri, cur_L, cur_w, res)
+                             : fail(AMX_ECUDA, "amx_em_fit: sample upload: %s", cudaGetErrorString(ce));
+  ws_free(x_dev);
   return rc;
 }
 

@@ -1,0 +1,749 @@
+// amx_em2.cuh -- K2, second generation: the fused CEM^2 component step as a warp-specialised streaming kernel.
+// Included by amx_em.cu (inside namespace amx, after the first-generation kernel whose control structures,
+// Cholesky routine and mbarrier/TMA helpers it shares).  Same algorithm, same pass sequence and the same
+// arithmetic per sample as em_fit_kernel's fused mode (automix.c:664-1006); what changes is how the work is laid on
+// the SM and how the GPUs (and the CTAs of one GPU) agree on the next step.
+//
+//  * ONE persistent CTA per SM: NTEAM teams of 128 threads over a ring of 128-sample stages (d coordinate rows of xT
+//    and the L live rows of the density cache E, 1 KB bulk copies, byte-counted on an mbarrier) that fills the SM's
+//    shared memory.  Tiles go to the teams round-robin; a team takes its stage as soon as it has landed and, when
+//    done with it, refills the same stage itself with the tile NS places ahead.  No CTA-wide barrier inside a
+//    pass, no producer to wait for, no idle SM while a tile is in flight: HBM latency is covered by the ring, not by
+//    occupancy.  (12 warps = a whole number of register-file allocation units: 168 registers per thread.)
+//  * Every accumulator lives in REGISTERS.  A-phase (thread = sample): new density of the refreshed component,
+//    sum_l lam_l E_il, T_l += E_il / sum (column sums are lam_l T_l: one FMA per component instead of
+//    multiply-multiply-add), log-likelihood; the thread leaves w_next and dx = x - pivot in the stage.  B-phase: the
+//    four warps of the team split the d + d(d+1)/2 entries of S1, S2 of the NEXT component four ways, each warp
+//    walking all 128 samples of the stage.  (The first generation reduced columns of the shared tile: three shared
+//    loads per FMA, which is what bound it.)
+//  * The step barrier has no leader and no release: the last CTA of a GPU to arrive sums that GPU's partial rows
+//    (value-major, coalesced, fixed order) and posts the row to EVERY GPU (peer stores over NVLink); every CTA of
+//    every GPU then adds the rows in GPU order and runs the sequential section -- weight update, annihilation,
+//    Cholesky, MML cost, convergence -- redundantly on its own copy of the mixture in shared memory.  Same inputs,
+//    same order of operations: every CTA takes the same branches, bit for bit, and nothing has to be published.
+//    One cross-GPU latency per step instead of three (arrive, leader's peer loads, public-state push).
+#pragma once
+
+constexpr int kV2TS = 128;                        // samples per stage
+constexpr int kV2NV = 128;                        // doubles per partial row (>= kEmLmax + 2 + 12 + 78)
+constexpr int kV2Dmax = 12;
+
+struct V2Sync {                                   // one per GPU, in that GPU's memory
+  unsigned arrive;                                // CTAs of this GPU that have finished the pass (monotonic)
+  unsigned pad0[31];
+  unsigned flag[kEmMaxDev][32];                   // flag[g][0] = epoch + 1 once GPU g's row of that epoch is in inbox
+  double inbox[2][kEmMaxDev][kV2NV];              // by epoch parity
+};
+
+struct V2Args {
+  V2Sync *sync[kEmMaxDev];                        // every GPU's block, peer-mapped
+  double *part;                                   // [kV2NV][grid] value-major partial rows of this GPU's CTAs
+  int ns;                                         // ring stages
+  int region0_doubles;                            // ring / reduction scratch (aliased)
+  int debug;
+};
+
+template <int DMAX>
+struct V2Cfg {
+  static constexpr int TRI = DMAX * (DMAX + 1) / 2;
+  static constexpr int NE = TRI + DMAX;           // S2 entries then S1 entries
+  static constexpr int NB = (NE + 3) / 4;         // per thread of a B-phase warp
+};
+
+__device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait with a watchdog: a copy that never lands becomes a trap (an error the host sees), not a hang
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 20000000000LL) __trap();
+  } while (!ok);
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// lnormprob of sample column `s` of a stage under component l, operation for operation the reference's
+// (automix.c:1727-1750), from the CTA's own copy of the mixture (see lnormprob_slow of the first generation).
+// xcol points at the x rows of the stage; they hold x itself (the caller runs this before the pivot shift).
+__device__ __noinline__ double v2_lnormprob_slow(const double *mu, const double *B, int d, const double *xcol) {
+  double r[kV2Dmax];
+  double det = 1.0;
+  for (int i = 0; i < d; i++) r[i] = xcol[i * kV2TS] - mu[i];
+  for (int i = 0; i < d; i++) {
+    for (int j = 0; j < i; j++) r[i] -= B[AMX_TRI(i, j)] * r[j];
+    const double bii = B[AMX_TRI(i, i)];
+    r[i] /= bii;
+    det *= bii;
+  }
+  double q = 0.0;
+  for (int i = 0; i < d; i++) q += r[i] * r[i];
+  return -0.5 * q - (d / 2.0) * log(2.0 * 3.14159265358979323846) - log(det);
+}
+
+// B-phase of one sample for the warp that owns entries e = WQ (mod 4): S2 (packed lower triangle, row-major) first,
+// then S1.  dxs: the stage's coordinate rows, already shifted by the pivot.
+template <int DMAX, int WQ>
+__device__ __forceinline__ void v2_moments(double (&acc)[V2Cfg<DMAX>::NB], const double *dxs, double w, int s, int d) {
+  constexpr int TRI = V2Cfg<DMAX>::TRI;
+  double dx[DMAX];
+#pragma unroll
+  for (int j = 0; j < DMAX; j++) dx[j] = (j < d) ? dxs[j * kV2TS + s] : 0.0;
+  int e = 0;
+#pragma unroll
+  for (int j = 0; j < DMAX; j++) {
+    const double wd = w * dx[j];
+#pragma unroll
+    for (int k = 0; k <= j; k++, e++)
+      if ((e & 3) == WQ) acc[e >> 2] = fma(wd, dx[k], acc[e >> 2]);
+    if (((TRI + j) & 3) == WQ) acc[(TRI + j) >> 2] += wd;
+  }
+}
+template <int DMAX, int WQ>
+__device__ __forceinline__ void v2_bphase(double (&acc)[V2Cfg<DMAX>::NB], const double *dxs, const double *ws, int lane, int d) {
+#pragma unroll 1
+  for (int q = 0; q < kV2TS / 32; q++) {
+    const int s = lane + 32 * q;
+    v2_moments<DMAX, WQ>(acc, dxs, ws[s], s, d);
+  }
+}
+
+// in-place removal of component `gone` from the CTA's mixture (:823-836, :908-921)
+template <int DMAX>
+__device__ __forceinline__ void v2_drop(LeaderS<DMAX> &S, double *s_mu, double *s_B, int d, int gone) {
+  const int t = threadIdx.x, nt = blockDim.x, tri = d * (d + 1) / 2, L = S.L;
+  for (int q = t; q < tri; q += nt)
+    for (int l = gone; l < L - 1; l++) s_B[l * tri + q] = s_B[(l + 1) * tri + q];
+  if (t < d)
+    for (int l = gone; l < L - 1; l++) s_mu[l * d + t] = s_mu[(l + 1) * d + t];
+  __syncthreads();
+  if (t == 0) {
+    for (int l = gone; l < L - 1; l++) {
+      S.lam[l] = S.lam[l + 1];
+      S.slot[l] = S.slot[l + 1];
+    }
+    S.L = L - 1;
+  }
+  __syncthreads();
+}
+
+template <int DMAX>
+__device__ __forceinline__ void v2_make_rec(LeaderS<DMAX> &S, const double *s_mu, double *s_rec, int d, int l) {
+  const int t = threadIdx.x, tri = d * (d + 1) / 2;
+  if (t == 0) {
+    double prod = 1.0;
+    for (int i = 0; i < d; i++) prod *= S.Bc[AMX_TRI(i, i)];
+    const double ld = log(prod);
+    s_rec[0] = S.lam[l];
+    s_rec[1] = 0.0;
+    s_rec[2] = ld;
+    s_rec[3] = -(d / 2.0) * log(2.0 * 3.14159265358979323846) - ld;
+  }
+  if (t < d) {
+    s_rec[AMX_REC_HEAD + t] = s_mu[l * d + t];
+    s_rec[AMX_REC_HEAD + d + t] = 1.0 / S.Bc[AMX_TRI(t, t)];
+  }
+  for (int q = t; q < tri; q += blockDim.x) s_rec[AMX_REC_HEAD + 2 * d + q] = S.Bc[q];
+}
+
+// The sequential section, run by every CTA on its own copy of the state (see the header).  Mirrors em_leader_block
+// branch for branch; `writer` (GPU 0, CTA 0) also records what the host reads back: traces and the best mixture.
+template <int DMAX>
+__device__ void v2_leader(const EmArgs &a, EmCtrl *c, bool writer, int pass, const double *s_tot, LeaderS<DMAX> &S,
+                          double *s_mu, double *s_B, double *s_rec) {
+  const int t = threadIdx.x, nt = blockDim.x, d = a.d, tri = d * (d + 1) / 2, nparams = d + tri;
+  if (t == 0) {
+    S.act = kActDone;
+    S.keep = 0;
+    S.drop = -1;
+    S.savebest = 0;
+    S.chol_ok = 1;
+  }
+  __syncthreads();
+  if (pass == kPassInitStats) {
+    // :700-723 common isotropic start; s_tot = [sum x_j (d) | sum x_j^2 (d)]
+    if (t == 0) {
+      double s2 = 0.0;
+      const double len = (double)a.n_total;
+      for (int j = 0; j < d; j++) s2 += (s_tot[d + j] - s_tot[j] * s_tot[j] / len) / len;
+      s2 /= (10.0 * d);
+      S.scal = sqrt(s2);
+      if (!(s2 > 0.0)) S.status = AMX_ENUMERIC;
+      S.L = a.Lmax;
+      S.c = a.Lmax;  // every start density is formed by the first E-step itself
+      S.next = 0;
+      S.iters = 0;
+      S.pass = kPassRefresh0;
+    }
+    __syncthreads();
+    for (int q = t; q < a.Lmax * d; q += nt) s_mu[q] = ld_cg(a.init_rows + q);
+    for (int q = t; q < a.Lmax * tri; q += nt) s_B[q] = 0.0;
+    __syncthreads();
+    for (int q = t; q < a.Lmax * d; q += nt) s_B[(q / d) * tri + AMX_TRI(q % d, q % d)] = S.scal;
+    if (t < kEmLmax) {
+      S.slot[t] = t;
+      S.lam[t] = (t < a.Lmax) ? 1.0 / a.Lmax : 0.0;
+    }
+    for (int q = t; q < tri; q += nt) S.Bc[q] = 0.0;
+    __syncthreads();
+    if (t < d) S.Bc[AMX_TRI(t, t)] = S.scal;
+    __syncthreads();
+    v2_make_rec<DMAX>(S, s_mu, s_rec, d, 0);
+  } else {
+    // a refresh finished: s_tot = [T_l (Lmax) | loglik | fallbacks | S1 (d) | S2 (tri)], column sums are lam_l T_l
+    if (t < kEmLmax) S.colsum[t] = (t < S.L) ? S.lam[t] * s_tot[t] : 0.0;
+    if (t < d) S.S1[t] = s_tot[kEmLmax + 2 + t];
+    for (int q = t; q < tri; q += nt) S.S2[q] = s_tot[kEmLmax + 2 + d + q];
+    if (t == 0) {
+      S.loglik = s_tot[kEmLmax] - 500.0 * s_tot[kEmLmax + 1];
+      if (S.iters == 0) {  // initial E-step done: start outer iteration 1
+        S.iters = 1;
+        S.natural = S.forced = 0;
+        S.c = 0;
+        S.act = kActPlan;
+      } else if (S.forced_pending) {  // refresh after a forced annihilation (:931-958)
+        S.act = kActFinishIter;
+      } else {
+        if (pass == kPassDensRefresh) S.c++;  // component kept: move on (:819)
+        S.act = (S.c < S.L) ? kActPlan : kActEndSweep;
+      }
+    }
+    __syncthreads();
+    if (S.forced_pending) {
+      leader_cost<DMAX>(S, a.n_total, nparams);
+      if (t == 0) S.forced_pending = 0;
+      __syncthreads();
+    }
+    while (S.act != kActDone) {
+      const int act = S.act;
+      __syncthreads();
+      if (act == kActPlan) {
+        const int cc = S.c;
+        if (t == 0) {
+          double tot = 0.0, wkeep = 0.0;
+          for (int l = 0; l < S.L; l++) {
+            const double wl = max_m(0.0, (S.colsum[l] - nparams / 2.0));
+            if (l == cc) wkeep = wl;
+            tot += wl;
+          }
+          S.lam[cc] = wkeep / tot;
+          S.comp_steps++;
+          S.flops += (double)a.n_total * (2.0 * d * d + 8.0 * d + 4.0 * S.L + 7.0);
+        }
+        __syncthreads();
+        leader_renorm<DMAX>(S);
+        if (S.lam[cc] > 0.005) {
+          // S1, S2 are moments of (x - pivot), pivot = the component's mean before this update:
+          //   mean = pivot + S1/S0,   cov = S2/S0 - (S1/S0)(S1/S0)^T   (:797-810 in shifted form)
+          const double S0 = S.colsum[cc];
+          if (t < d) {
+            S.dl[t] = S.S1[t] / S0;
+            s_mu[cc * d + t] = s_mu[cc * d + t] + S.dl[t];
+          }
+          __syncthreads();
+          for (int q = t; q < tri; q += nt) {
+            int j = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+            while ((j + 1) * (j + 2) / 2 <= q) j++;
+            while (j * (j + 1) / 2 > q) j--;
+            const int k = q - j * (j + 1) / 2;
+            S.Bc[q] = (S.S2[q] - S.S1[j] * S.dl[k]) / S0;
+          }
+          __syncthreads();
+          if (t < 32) {
+            const bool ok = warp_chol<DMAX>(S.Bc, d);
+            if (t == 0) S.chol_ok = ok ? 1 : 0;
+          }
+          __syncthreads();
+          for (int q = t; q < tri; q += nt) s_B[cc * tri + q] = S.Bc[q];
+          v2_make_rec<DMAX>(S, s_mu, s_rec, d, cc);
+          if (t == 0) {
+            if (!S.chol_ok) {
+              S.status = AMX_ENUMERIC;
+              S.stop = 1;
+              S.pass = kPassStop;
+            } else {
+              S.next = (cc + 1 < S.L) ? cc + 1 : 0;
+              S.pass = kPassDensRefresh;
+            }
+            S.act = kActDone;
+          }
+        } else {  // natural annihilation (:821-845)
+          v2_drop<DMAX>(S, s_mu, s_B, d, cc);
+          leader_renorm<DMAX>(S);
+          if (t == 0) {
+            S.natural = 1;
+            S.next = (cc < S.L) ? cc : 0;
+            S.pass = kPassRefresh;
+            S.act = kActDone;
+          }
+        }
+      } else if (act == kActEndSweep) {
+        leader_cost<DMAX>(S, a.n_total, nparams);
+        if (t == 0) {
+          if (S.iters == 1) S.cost_prev = S.cost;
+          S.savebest = (S.iters == 1 || S.cost < S.cost_best) ? 1 : 0;  // :881-893
+          if (S.savebest) {
+            S.best_L = S.L;
+            S.cost_best = S.cost;
+          }
+          S.drop = -1;
+          if (fabs(S.cost_prev - S.cost) < min_m(1E-5 * fabs(S.cost_prev), 0.01) && S.iters > 1) {  // :894
+            if (S.L == 1) {
+              S.stop = 1;
+            } else {
+              S.forced = 2;
+              double lo = S.lam[0];
+              int gone = 0;
+              for (int l = 1; l < S.L; l++)
+                if (lo > S.lam[l]) {
+                  lo = S.lam[l];
+                  gone = l;
+                }
+              S.drop = gone;
+            }
+          }
+        }
+        __syncthreads();
+        if (S.savebest && writer) {
+          if (t < S.L) c->best_lam[t] = S.lam[t];
+          for (int q = t; q < S.L * d; q += nt) c->best_mu[q / d][q % d] = s_mu[q];
+          for (int q = t; q < S.L * tri; q += nt) c->best_B[q / tri][q % tri] = s_B[q];
+        }
+        __syncthreads();
+        if (S.drop >= 0) {
+          v2_drop<DMAX>(S, s_mu, s_B, d, S.drop);
+          leader_renorm<DMAX>(S);
+          if (t == 0) {
+            S.forced_pending = 1;
+            S.next = 0;
+            S.pass = kPassRefresh;
+            S.act = kActDone;
+          }
+        } else if (t == 0) {
+          S.act = kActFinishIter;
+        }
+      } else {  // kActFinishIter (:961-970)
+        if (t == 0) {
+          if (S.iters > a.maxit) S.stop = 1;
+          S.cost_prev = S.cost;
+          const int it = S.iters - 1;
+          if (writer) {
+            if (a.trace_ann) a.trace_ann[it] = S.natural + S.forced;
+            if (a.trace_cost) a.trace_cost[it] = S.cost;
+            if (a.trace_loglik) a.trace_loglik[it] = S.loglik;
+            if (a.trace_L) a.trace_L[it] = S.L;
+          }
+          if (S.stop) {
+            S.pass = kPassStop;
+            S.act = kActDone;
+          } else {
+            S.iters++;
+            S.natural = S.forced = 0;
+            S.c = 0;
+            S.act = kActPlan;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------------------
+template <int DMAX, int NTEAM>
+__global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2Args v) {
+  using CF = V2Cfg<DMAX>;
+  constexpr int TRI = CF::TRI, NB = CF::NB;
+  constexpr int NCONS = NTEAM * 128;
+  constexpr int kMaxStages = 8;
+  extern __shared__ __align__(128) double smem[];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages];
+  __shared__ int s_flag;
+
+  const int d = a.d, Lmax = a.Lmax, tri = d * (d + 1) / 2;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int team = warp >> 2, wq = warp & 3, tt = t & 127;
+  const long n = a.n, np = a.npad;
+  const long ntiles = np / kV2TS;
+  const int G = (int)gridDim.x;
+  const bool writer = (a.rank == 0 && blockIdx.x == 0);
+  EmCtrl *ctrl = a.ctrl;
+
+  // shared memory: [region0: ring, aliased by the end-of-pass reduction scratch][mu][B][rec][tot][part][LeaderS]
+  const int stage_doubles = (d + Lmax + 1) * kV2TS;  // rows: x (d) | E (Lmax, component order) | w_next
+  double *ring = smem;
+  double *s_mu = smem + v.region0_doubles;           // [Lmax][d]
+  double *s_B = s_mu + Lmax * d;                     // [Lmax][tri]
+  double *s_rec = s_B + Lmax * tri;                  // family record of the component in progress
+  double *s_tot = s_rec + (AMX_REC_HEAD + 2 * DMAX + TRI);  // [kV2NV] totals over all CTAs and GPUs
+  double *s_part = s_tot + kV2NV;                    // [kV2NV] this CTA's partial row
+  LeaderS<DMAX> &S = *reinterpret_cast<LeaderS<DMAX> *>(s_part + kV2NV);
+  const int NS = v.ns;
+
+  if (t == 0) {
+    for (int q = 0; q < NS; q++) mbar_init(&s_full[q], 1);
+    memset(&S, 0, sizeof(S));
+  }
+  for (int q = t; q < kV2NV; q += blockDim.x) s_part[q] = 0.0;
+  __syncthreads();
+
+  unsigned epoch = 0;
+  unsigned long long seq_base = 0;  // stages used by the passes so far (ring position and mbarrier parity)
+  int pass = kPassInitStats;
+  long long dbg_pass = 0, dbg_bar = 0, dbg_lead = 0;
+
+  for (;;) {
+    const long long tk0 = clock64();
+    int nv = 0;
+    if (pass == kPassInitStats) {
+      // transpose x -> xT and accumulate sum x_j, sum x_j^2 (:700-711)
+      double acc[2 * DMAX];
+#pragma unroll
+      for (int j = 0; j < 2 * DMAX; j++) acc[j] = 0.0;
+      {
+        for (long i = (long)blockIdx.x * NCONS + t; i < n; i += (long)G * NCONS) {
+#pragma unroll
+          for (int j = 0; j < DMAX; j++)
+            if (j < d) {
+              const double xv = a.x[i * d + j];
+              __stcg(a.xT + (size_t)j * np + i, xv);
+              acc[j] += xv;
+              acc[DMAX + j] = fma(xv, xv, acc[DMAX + j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2 * DMAX; j++) {
+          const double r = warp_sum(acc[j]);
+          if (lane == 0) ring[warp * 2 * DMAX + j] = r;
+        }
+      }
+      __syncthreads();
+      if (t < 2 * d) {
+        const int src = t < d ? t : DMAX + (t - d);
+        double tot = 0.0;
+        for (int w = 0; w < 4 * NTEAM; w++) tot += ring[w * 2 * DMAX + src];
+        s_part[t] = tot;
+      }
+      fence_proxy_async();
+      nv = 2 * d;
+    } else {
+      // ------------------------------------------------------------ the streaming pass
+      const int L = S.L < 0 ? 0 : S.L, nx = S.next, cc = S.c;
+      const bool dens_all = (pass == kPassRefresh0);  // first E-step: every density is formed here, unguarded weights
+      const bool dens = (pass == kPassDensRefresh);
+      const int ntile_cta = (int)((ntiles - (long)blockIdx.x + G - 1) / G);  // tiles b, b+G, ... of this CTA
+      const int rows = dens_all ? d : d + L - (dens ? 1 : 0);
+      // one warp's lanes issue the row copies of tile `it` of this CTA into stage (seq_base + it) % NS
+      auto fetch = [&](int it) {
+        const unsigned long long seq = seq_base + (unsigned long long)it;
+        const int st = (int)(seq % (unsigned)NS);
+        double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS;
+        const long tl = (long)blockIdx.x + (long)it * G;
+        if (lane == 0) mbar_expect_tx(&s_full[st], (uint32_t)(rows * kV2TS * 8));
+        __syncwarp();
+        for (int q = lane; q < d + (dens_all ? 0 : L); q += 32) {
+          if (q < d) {
+            tma_load_row(xs + q * kV2TS, a.xT + (size_t)q * np + tl * kV2TS, kV2TS * 8, &s_full[st]);
+          } else {
+            const int l = q - d;
+            if (!(dens && l == cc))
+              tma_load_row(Es + l * kV2TS, a.E + (size_t)S.slot[l] * np + tl * kV2TS, kV2TS * 8, &s_full[st]);
+          }
+        }
+      };
+      // prologue: the ring is idle (end-of-pass barrier): warp 0 fills it
+      fence_proxy_async();
+      if (warp == 0)
+        for (int it = 0; it < NS && it < ntile_cta; it++) fetch(it);
+      {
+        double accT[kEmLmax];  // T_l = sum_i E_il / sum_i  (column sum of the responsibilities = lam_l T_l)
+        double accB[NB];
+#pragma unroll
+        for (int l = 0; l < kEmLmax; l++) accT[l] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NB; q++) accB[q] = 0.0;
+        double ll = 0.0, nfb = 0.0;
+        const int cslot = dens ? S.slot[cc] : 0;
+        const double *lam = S.lam;
+        for (int it = team; it < ntile_cta; it += NTEAM) {
+          const unsigned long long seq = seq_base + (unsigned long long)it;
+          const int st = (int)(seq % (unsigned)NS);
+          double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS, *ws = Es + Lmax * kV2TS;
+          const long tl = (long)blockIdx.x + (long)it * G;
+          const long i = tl * kV2TS + tt;
+          const bool valid = i < n;
+          mbar_wait_wd(&s_full[st], (uint32_t)((seq / NS) & 1ull));
+          // ---- A-phase: thread tt owns sample tt of the stage
+          double *Ecol = Es + tt;
+          double xv[DMAX];
+#pragma unroll
+          for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? xs[j * kV2TS + tt] : 0.0;
+          if (dens_all) {
+            const double rd = s_rec[AMX_REC_HEAD + d], c1 = s_rec[3];  // all start factors are sqrt(s2) I
+            for (int l = 0; l < L; l++) {
+              const double *mu = s_mu + l * d;
+              double q = 0.0;
+#pragma unroll
+              for (int j = 0; j < DMAX; j++)
+                if (j < d) {
+                  const double r = (xv[j] - mu[j]) * rd;
+                  q = fma(r, r, q);
+                }
+              const double e = exp(fma(-0.5, q, c1));
+              Ecol[l * kV2TS] = e;
+              if (valid) __stcg(a.E + (size_t)S.slot[l] * np + i, e);
+            }
+          } else if (dens) {
+            double r[DMAX];
+            const double enew = exp(fma(-0.5, solve_lower<DMAX, true>(s_rec, d, xv, r), s_rec[3]));
+            Ecol[cc * kV2TS] = enew;
+            if (valid) __stcg(a.E + (size_t)cslot * np + i, enew);
+          }
+          // sum_l lam_l E_il in component order (as the reference adds them)
+          double sum = 0.0;
+          for (int l = 0; l < L; l++) sum = fma(lam[l], Ecol[l * kV2TS], sum);
+          double wn = 0.0;
+          if (!valid) {
+            // padding sample: no weight anywhere
+          } else if (dens_all) {
+            // First E-step: w = lam * pdf / sum with no look at the sum, as the reference does (:737-745); 0/0 = NaN
+            // poisons the column sums and components are annihilated until a guarded refresh clears it.
+#pragma unroll
+            for (int l = 0; l < kEmLmax; l++)
+              if (l < L) {
+                const double w = (lam[l] * Ecol[l * kV2TS]) / sum;
+                accT[l] += w / lam[l];
+                if (l == nx) wn = w;
+              }
+          } else if (sum >= 1e-280) {  // the reference's guard (:855-866) holds, and 1/sum is safe
+            const double inv = 1.0 / sum;
+            ll += log(sum);
+#pragma unroll
+            for (int l = 0; l < kEmLmax; l++)
+              if (l < L) accT[l] = fma(Ecol[l * kV2TS], inv, accT[l]);
+            wn = (lam[nx] * Ecol[nx * kV2TS]) * inv;
+          } else if (sum < 1e-280) {
+            // Every component puts this sample below exp(-644): cached densities near the subnormal range, where
+            // lam * exp(lpd) no longer tracks the reference's exp(log(lam) + lpd) (nor can 1/sum be formed).
+            // Redo the sample the reference's way from the components' parameters (:849-866).
+            double s2 = 0.0;
+            for (int l = 0; l < L; l++) {
+              const double wl = exp(log(lam[l]) + v2_lnormprob_slow(s_mu + l * d, s_B + l * tri, d, xs + tt));
+              Ecol[l * kV2TS] = wl;
+              s2 += wl;
+            }
+            if (s2 > 0) {
+              ll += log(s2);
+#pragma unroll
+              for (int l = 0; l < kEmLmax; l++)
+                if (l < L) {
+                  const double w = Ecol[l * kV2TS] / s2;
+                  accT[l] += (lam[l] > 0.0) ? w / lam[l] : 0.0;
+                  if (l == nx) wn = w;
+                }
+            } else {
+              nfb += 1.0;
+              const double w = 1.0 / L;
+#pragma unroll
+              for (int l = 0; l < kEmLmax; l++)
+                if (l < L) accT[l] += (lam[l] > 0.0) ? w / lam[l] : 0.0;
+              wn = (L > 0) ? w : 0.0;
+            }
+          } else {  // NaN sum: the reference's `sum > 0` fails -> uniform responsibilities and the -500 penalty
+            nfb += 1.0;
+            const double w = 1.0 / L;
+#pragma unroll
+            for (int l = 0; l < kEmLmax; l++)
+              if (l < L) accT[l] += (lam[l] > 0.0) ? w / lam[l] : 0.0;
+            wn = (L > 0) ? w : 0.0;
+          }
+          ws[tt] = wn;
+          // shift by the pivot (current mean of the next component): the rows become dx = x - pivot
+          {
+            const double *piv = s_mu + nx * d;
+#pragma unroll
+            for (int j = 0; j < DMAX; j++)
+              if (j < d) xs[j * kV2TS + tt] = valid ? xv[j] - piv[j] : 0.0;
+          }
+          named_bar(1 + team, 128);
+          // ---- B-phase: warp wq owns the entries e = wq (mod 4) of (S2 | S1) over all 128 samples
+          if (wq == 0) v2_bphase<DMAX, 0>(accB, xs, ws, lane, d);
+          else if (wq == 1) v2_bphase<DMAX, 1>(accB, xs, ws, lane, d);
+          else if (wq == 2) v2_bphase<DMAX, 2>(accB, xs, ws, lane, d);
+          else v2_bphase<DMAX, 3>(accB, xs, ws, lane, d);
+          // the stage is free once all four warps are through; the team refills it with the tile NS places ahead
+          fence_proxy_async();
+          named_bar(1 + team, 128);
+          if (wq == 0 && it + NS < ntile_cta) fetch(it + NS);
+        }
+        // ---- end of pass: the teams' register accumulators -> this CTA's partial row, in a fixed order.
+        // Lanes are first folded four to one by shuffles; the 8 x 4 NTEAM group sums per value go through the
+        // (now idle) ring memory.
+        named_bar(8, NCONS);  // every stage has been consumed
+        constexpr int NG = NCONS / 4;  // group writers
+        double *scrA = ring;                      // [kEmLmax + 2][NG]
+        double *scrB = ring + (kEmLmax + 2) * NG;  // [4 NB][NG / 4]: entry e = 4 i + wq, writers of the same wq
+        const int grp = t >> 2;
+#pragma unroll
+        for (int l = 0; l < kEmLmax + 2; l++) {
+          double r = (l < kEmLmax) ? accT[l < kEmLmax ? l : 0] : (l == kEmLmax ? ll : nfb);
+          r += __shfl_xor_sync(0xffffffffu, r, 1);
+          r += __shfl_xor_sync(0xffffffffu, r, 2);
+          if ((lane & 3) == 0) scrA[l * NG + grp] = r;
+        }
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+          double r = accB[q];
+          r += __shfl_xor_sync(0xffffffffu, r, 1);
+          r += __shfl_xor_sync(0xffffffffu, r, 2);
+          if ((lane & 3) == 0) scrB[(4 * q + wq) * (NG / 4) + team * 8 + (lane >> 2)] = r;
+        }
+        named_bar(8, NCONS);
+        for (int l = warp; l < kEmLmax + 2; l += 4 * NTEAM) {
+          double r = 0.0;
+          for (int g = lane; g < NG; g += 32) r += scrA[l * NG + g];
+          r = warp_sum(r);
+          if (lane == 0) s_part[l] = r;
+        }
+        for (int e = warp; e < TRI + DMAX; e += 4 * NTEAM) {
+          double r = (lane < NG / 4) ? scrB[e * (NG / 4) + lane] : 0.0;
+          r = warp_sum(r);
+          // entry e of the DMAX-packed (S2 | S1) -> position in the partial row: S1 first, then the d-packed triangle
+          // (rows j < d of the packed triangle are its first tri(d) entries in either packing)
+          if (lane == 0) {
+            if (e >= TRI) {
+              if (e - TRI < d) s_part[kEmLmax + 2 + (e - TRI)] = r;
+            } else if (e < tri) {
+              s_part[kEmLmax + 2 + d + e] = r;
+            }
+          }
+        }
+      }
+      seq_base += (unsigned long long)ntile_cta;
+      nv = kEmLmax + 2 + d + tri;
+      fence_proxy_async();  // the ring was used as plain scratch: order that before the next pass's bulk copies
+      __syncthreads();
+    }
+
+    // ------------------------------------------------------------------ exchange: partial rows -> totals everywhere
+    const long long tk1 = clock64();
+    V2Sync *me = v.sync[a.rank];
+    for (int q = t; q < nv; q += blockDim.x) __stcg(v.part + (size_t)q * G + blockIdx.x, s_part[q]);
+    __syncthreads();
+    if (t == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(&me->arrive, 1u);
+      s_flag = (prev == (unsigned)G * (epoch + 1u) - 1u) ? 1 : 0;
+      if (s_flag) __threadfence();
+    }
+    __syncthreads();
+    const int par = (int)(epoch & 1u);
+    if (s_flag) {
+      // last CTA of this GPU: sum the GPU's partial rows (lanes over consecutive CTAs of one value: coalesced;
+      // fixed order), then post the row to every GPU's inbox and raise this GPU's flag there
+      for (int q = warp; q < nv; q += (int)(blockDim.x >> 5)) {
+        const double *src = v.part + (size_t)q * G;
+        double r = 0.0;
+        for (int b = lane; b < G; b += 32) r += ld_cg(src + b);
+        r = warp_sum(r);
+        if (lane == 0) s_tot[q] = r;
+      }
+      __syncthreads();
+      for (int q = t; q < nv * a.ndev; q += blockDim.x) {
+        const int g = q / nv, k = q - g * nv;
+        v.sync[g]->inbox[par][a.rank][k] = s_tot[k];
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (t < a.ndev) st_release_sys(&v.sync[t]->flag[a.rank][0], epoch + 1u);
+    }
+    if (t < a.ndev) {  // every CTA: wait until every GPU's row of this epoch is in the local inbox
+      const unsigned *f = &me->flag[t][0];
+      const long long t0 = clock64();
+      unsigned ns = 20;
+      while (ld_acquire_sys(f) < epoch + 1u) {
+        __nanosleep(ns);
+        if (ns < 160) ns *= 2;
+        if (clock64() - t0 > 40000000000LL) {  // ~20 s: a partner is gone
+          S.status = AMX_ECUDA;
+          S.stop = 2;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (S.stop == 2) {
+      if (writer && t == 0) atomicExch(&ctrl->status, AMX_ECUDA);
+      return;
+    }
+    for (int q = t; q < nv; q += blockDim.x) {  // rows in GPU order: the same sum on every CTA of every GPU
+      double r = 0.0;
+      for (int g = 0; g < a.ndev; g++) r += ld_cg(&me->inbox[par][g][q]);
+      s_tot[q] = r;
+    }
+    epoch++;
+    __syncthreads();
+    const long long tk2 = clock64();
+    v2_leader<DMAX>(a, ctrl, writer, pass, s_tot, S, s_mu, s_B, s_rec);
+    const long long tk3 = clock64();
+    dbg_pass += tk1 - tk0;
+    dbg_bar += tk2 - tk1;
+    dbg_lead += tk3 - tk2;
+    pass = S.pass;
+    if (pass == kPassStop) break;
+  }
+
+  // what the host reads back (GPU 0, CTA 0)
+  if (writer) {
+    if (t == 0) {
+      ctrl->pass = S.pass; ctrl->L = S.L; ctrl->c = S.c; ctrl->next = S.next; ctrl->iters = S.iters; ctrl->stop = S.stop;
+      ctrl->status = S.status; ctrl->best_L = S.best_L; ctrl->comp_steps = S.comp_steps; ctrl->flops = S.flops;
+      ctrl->loglik = S.loglik; ctrl->cost = S.cost; ctrl->cost_prev = S.cost_prev; ctrl->cost_best = S.cost_best;
+      ctrl->dbg[0] = dbg_pass; ctrl->dbg[1] = dbg_bar; ctrl->dbg[3] = dbg_lead;
+    }
+    const int Lw = S.L < 0 ? 0 : S.L;
+    if (t < kEmLmax) {
+      ctrl->lam[t] = S.lam[t];
+      ctrl->slot[t] = S.slot[t];
+    }
+    for (int q = t; q < Lw * d; q += blockDim.x) ctrl->mu[q / d][q % d] = s_mu[q];
+    for (int q = t; q < Lw * tri; q += blockDim.x) ctrl->B[q / tri][q % tri] = s_B[q];
+  }
+  // optional dump of the responsibilities of the working state (step-parity tests)
+  if (a.w_out != nullptr) {
+    const int L = S.L;
+    for (long i = (long)blockIdx.x * blockDim.x + t; i < n; i += (long)G * blockDim.x) {
+      double sum = 0.0;
+      for (int l = 0; l < L; l++) sum += S.lam[l] * __ldcg(a.E + (size_t)S.slot[l] * np + i);
+      for (int l = 0; l < L; l++) {
+        const double e = __ldcg(a.E + (size_t)S.slot[l] * np + i);
+        a.w_out[(size_t)i * a.Lmax + l] = (sum > 0) ? S.lam[l] * e / sum : 1.0 / L;
+      }
+    }
+  }
+}
+
+template <int DMAX>
+constexpr size_t v2_fixed_doubles(int d, int Lmax) {
+  return (size_t)Lmax * d + (size_t)Lmax * (d * (d + 1) / 2) + (AMX_REC_HEAD + 2 * DMAX + V2Cfg<DMAX>::TRI) + 2 * kV2NV +
+         (sizeof(LeaderS<DMAX>) + 7) / 8 + 2;
+}
+template <int DMAX, int NTEAM>
+constexpr size_t v2_scratch_doubles() {
+  return (size_t)(kEmLmax + 2) * (NTEAM * 32) + (size_t)4 * V2Cfg<DMAX>::NB * (NTEAM * 8) + 64;
+}
