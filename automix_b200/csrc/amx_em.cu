@@ -1430,7 +1430,9 @@ template <int DMAX, int NTEAM>
 static int em2_plan_one(int d, int Lmax, size_t max_dyn, V2Plan *p) {
   const size_t fixed = v2_fixed_doubles<DMAX>(d, Lmax), scratch = v2_scratch_doubles<DMAX, NTEAM>();
   const size_t stage = (size_t)(d + Lmax + 1) * kV2TS;
-  const size_t avail = max_dyn / sizeof(double);
+  cudaFuncAttributes fa;
+  AMX_CUDA(cudaFuncGetAttributes(&fa, em_fit_v2_kernel<DMAX, NTEAM>));
+  const size_t avail = (max_dyn - fa.sharedSizeBytes - 64) / sizeof(double);
   if (avail < fixed + scratch + 2 * stage) return fail(AMX_ECUDA, "EM kernel does not fit in shared memory (d=%d, Lmax=%d)", d, Lmax);
   int ns = (int)((avail - fixed) / stage);
   if (ns > 8) ns = 8;
@@ -1453,16 +1455,20 @@ static int em2_launch_one(EmArgs &a, V2Args &v, unsigned grid, size_t smem, cuda
 }
 #define AMX_V2_DISPATCH(FN, ...)                                              \
   do {                                                                        \
-    if (nteam == 2) {                                                         \
-      if (d <= 4) return FN<4, 2>(__VA_ARGS__);                               \
-      if (d <= 8) return FN<8, 2>(__VA_ARGS__);                               \
-      if (d <= 10) return FN<10, 2>(__VA_ARGS__);                             \
-      return FN<12, 2>(__VA_ARGS__);                                          \
+    switch (d) {                                                              \
+      case 1: return FN<1, 3>(__VA_ARGS__);                                   \
+      case 2: return FN<2, 3>(__VA_ARGS__);                                   \
+      case 3: return FN<3, 3>(__VA_ARGS__);                                   \
+      case 4: return FN<4, 3>(__VA_ARGS__);                                   \
+      case 5: return FN<5, 3>(__VA_ARGS__);                                   \
+      case 6: return FN<6, 3>(__VA_ARGS__);                                   \
+      case 7: return FN<7, 3>(__VA_ARGS__);                                   \
+      case 8: return FN<8, 3>(__VA_ARGS__);                                   \
+      case 9: return FN<9, 3>(__VA_ARGS__);                                   \
+      case 10: return FN<10, 3>(__VA_ARGS__);                                 \
+      case 11: return FN<11, 3>(__VA_ARGS__);                                 \
+      default: return FN<12, 3>(__VA_ARGS__);                                 \
     }                                                                         \
-    if (d <= 4) return FN<4, 3>(__VA_ARGS__);                                 \
-    if (d <= 8) return FN<8, 3>(__VA_ARGS__);                                 \
-    if (d <= 10) return FN<10, 3>(__VA_ARGS__);                               \
-    return FN<12, 3>(__VA_ARGS__);                                            \
   } while (0)
 static int em2_plan(int d, int nteam, int Lmax, size_t max_dyn, V2Plan *p) { AMX_V2_DISPATCH(em2_plan_one, d, Lmax, max_dyn, p); }
 static int em2_launch(int d, int nteam, EmArgs &a, V2Args &v, unsigned grid, size_t smem, cudaStream_t st) {
@@ -1582,7 +1588,8 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   // second-generation kernel (amx_em2.cuh) wherever the fused step applies; AMX_EM_V2=0 keeps the first generation
   const char *v2e = getenv("AMX_EM_V2"), *v2t = getenv("AMX_EM_TEAMS");
   const bool use_v2 = fused && d <= kV2Dmax && (v2e ? atoi(v2e) != 0 : true);
-  const int nteam = (v2t && atoi(v2t) == 2) ? 2 : 3;
+  (void)v2t;
+  const int nteam = 3;  // 12 warps: a whole number of register-file allocation units at 168 registers
   V2Plan plan;
   memset(&plan, 0, sizeof(plan));
   if (use_v2) {
@@ -1590,14 +1597,14 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     AMX_CUDA(cudaDeviceGetAttribute(&max_dyn, cudaDevAttrMaxSharedMemoryPerBlockOptin, devs[0]));
     for (int g = 0; g < ndev; g++) {  // the attribute is per device
       AMX_CUDA(cudaSetDevice(devs[g]));
-      if (int prc = em2_plan(d, nteam, Lmax, (size_t)max_dyn - 256, &plan)) {
+      if (int prc = em2_plan(d, nteam, Lmax, (size_t)max_dyn, &plan)) {
         cudaSetDevice(home);
         return prc;
       }
     }
     if (const char *nse = getenv("AMX_EM_STAGES")) {
       const int want_ns = atoi(nse);
-      if (want_ns >= 2 && want_ns < plan.ns) plan.ns = want_ns;
+      if (want_ns >= 2 && want_ns < plan.ns) plan.ns = want_ns;  // (region0 keeps its size)
     }
     AMX_CUDA(cudaSetDevice(home));
   }
@@ -1712,12 +1719,7 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
       AMX_CUDA(cudaMemsetAsync(a.xT, 0, sizeof(double) * (size_t)d * a.npad, st[g]));
       AMX_CUDA(cudaMemsetAsync(a.E, 0, sizeof(double) * (size_t)Lmax * a.npad, st[g]));
       AMX_CUDA(cudaMemsetAsync(a.wnxt, 0, sizeof(double) * (size_t)a.npad, st[g]));
-    } else if (a.npad > a.n) {  // the tail of the last tile is read by the bulk copies (and ignored): keep it finite
-      for (int j = 0; j < d; j++)
-        AMX_CUDA(cudaMemsetAsync(a.xT + (size_t)j * a.npad + a.n, 0, sizeof(double) * (size_t)(a.npad - a.n), st[g]));
-      for (int l = 0; l < Lmax; l++)
-        AMX_CUDA(cudaMemsetAsync(a.E + (size_t)l * a.npad + a.n, 0, sizeof(double) * (size_t)(a.npad - a.n), st[g]));
-    }
+    }  // (the second generation ignores whatever the padding of the last tile holds)
     if (cur_w) AMX_CUDA(ws_malloc(&a.w_out, sizeof(double) * (size_t)a.n * Lmax));
     int per_sm = 0;
     if (use_v2) per_sm = 1;
@@ -1831,6 +1833,20 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
       res->kernel_ms = ms;
       res->flops = c->flops;
       res->bytes = 8.0 * d * (double)n * (double)c->comp_steps;
+    }
+    if (getenv("AMX_EM_DEBUG") && use_v2) {
+      V2Sync hs;
+      if (cudaMemcpy(&hs, v2sync[0], sizeof(hs), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        long long lo = hs.dbg_cta[0], hi = hs.dbg_cta[0];
+        double av = 0;
+        const int gg = A[0].dev[0].grid < 160 ? A[0].dev[0].grid : 160;
+        for (int b = 0; b < gg; b++) {
+          lo = hs.dbg_cta[b] < lo ? hs.dbg_cta[b] : lo;
+          hi = hs.dbg_cta[b] > hi ? hs.dbg_cta[b] : hi;
+          av += (double)hs.dbg_cta[b] / gg;
+        }
+        fprintf(stderr, "[em2 dbg] data-pass cycles per CTA: min %lld avg %.0f max %lld\n", lo, av, hi);
+      }
     }
     if (getenv("AMX_EM_DEBUG") && use_v2)
       fprintf(stderr, "[em2 dbg] %d GPU(s), %d teams, %d stages, %zu B smem; CTA 0 of GPU 0, cycles: data passes %lld | exchange %lld | sequential section %lld (%ld component steps)\n",

@@ -33,6 +33,7 @@ struct V2Sync {                                   // one per GPU, in that GPU's 
   unsigned pad0[31];
   unsigned flag[kEmMaxDev][32];                   // flag[g][0] = epoch + 1 once GPU g's row of that epoch is in inbox
   double inbox[2][kEmMaxDev][kV2NV];              // by epoch parity
+  long long dbg_cta[160];                         // AMX_EM_DEBUG: cycles each CTA spent in its data passes
 };
 
 struct V2Args {
@@ -43,11 +44,24 @@ struct V2Args {
   int debug;
 };
 
+// Data layout in HBM (second generation): TILE-major.  The d coordinate rows of a 128-sample tile are contiguous
+// (xT[tile][j][128]) and so are its Lmax density-cache rows (E[tile][slot][128]): a stage is filled by one bulk copy for
+// the coordinates plus one per run of consecutive live slots -- a handful of copies per tile instead of d + L.  (A bulk
+// copy costs the SM ~170 cycles whatever its size; at one 1 KB row per copy that alone was 3.5 times the HBM time of
+// the tile, and it is what bound the first generation too.)
+__device__ __forceinline__ size_t v2_x_at(long i, int j, int d) { return ((size_t)(i / kV2TS) * d + j) * kV2TS + (size_t)(i % kV2TS); }
+__device__ __forceinline__ size_t v2_e_at(long i, int slot, int Lmax) {
+  return ((size_t)(i / kV2TS) * Lmax + slot) * kV2TS + (size_t)(i % kV2TS);
+}
+
 template <int DMAX>
 struct V2Cfg {
   static constexpr int TRI = DMAX * (DMAX + 1) / 2;
-  static constexpr int NE = TRI + DMAX;           // S2 entries then S1 entries
-  static constexpr int NB = (NE + 3) / 4;         // per thread of a B-phase warp
+  static constexpr int NE = TRI + DMAX;                // S2 entries then S1 entries
+  static constexpr int NE4 = (NE + 3) / 4 * 4;         // ... padded so that the T entries keep l = e (mod 4)
+  static constexpr int NEALL = NE4 + kEmLmax;          // ... then T_l, l = 0 .. kEmLmax-1
+  static constexpr int NB = NEALL / 4;                 // accumulators per thread: entries e = wq (mod 4)
+  static constexpr int NBM = NE4 / 4;                  // of which moments
 };
 
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -95,14 +109,72 @@ __device__ __noinline__ double v2_lnormprob_slow(const double *mu, const double 
   return -0.5 * q - (d / 2.0) * log(2.0 * 3.14159265358979323846) - log(det);
 }
 
-// B-phase of one sample for the warp that owns entries e = WQ (mod 4): S2 (packed lower triangle, row-major) first,
-// then S1.  dxs: the stage's coordinate rows, already shifted by the pivot.
+// A sample whose total density is below 1e-280 (or NaN), redone the reference's way (:849-866): every component puts
+// it below exp(-644), the cached densities are near the subnormal range where lam * exp(lpd) no longer tracks the
+// reference's exp(log(lam) + lpd) and 1/sum cannot be formed.  Leaves w_l / lam_l in the sample's column of the stage
+// (the caller accumulates it with multiplier 1), returns the responsibility of component nx.
+__device__ __noinline__ double v2_slow_sample(const double *lam, const double *s_mu, const double *s_B, int d, int tri, int L,
+                                              int nx, double sum, const double *xcol, double *Ecol, double *ll, double *nfb) {
+  double wn = 0.0;
+  bool uniform = !(sum < 1e-280);  // NaN sum: the reference's `sum > 0` fails -> uniform responsibilities, -500 penalty
+  if (!uniform) {
+    double s2 = 0.0;
+    for (int l = 0; l < L; l++) {
+      const double wl = exp(log(lam[l]) + v2_lnormprob_slow(s_mu + l * d, s_B + l * tri, d, xcol));
+      Ecol[l * kV2TS] = wl;
+      s2 += wl;
+    }
+    if (s2 > 0) {
+      *ll += log(s2);
+      for (int l = 0; l < L; l++) {
+        const double w = Ecol[l * kV2TS] / s2;
+        Ecol[l * kV2TS] = (lam[l] > 0.0) ? w / lam[l] : 0.0;
+        if (l == nx) wn = w;
+      }
+    } else {
+      uniform = true;
+    }
+  }
+  if (uniform) {
+    *nfb += 1.0;
+    const double w = 1.0 / L;
+    for (int l = 0; l < L; l++) Ecol[l * kV2TS] = (lam[l] > 0.0) ? w / lam[l] : 0.0;
+    wn = (L > 0) ? w : 0.0;
+  }
+  return wn;
+}
+
+// |T^-1 (x - mu)|^2 for the lower-triangular factor of a family record (forward substitution of lnormprob,
+// automix.c:1735-1747).  Column-oriented: once r_j is known every later row takes its -T_ij r_j term, so row i
+// receives its terms in the order j = 0 .. i-1 exactly as in the row-oriented solve_lower (same roundings), but the
+// rows are d independent chains instead of one chain of d(d+1)/2 operations.
+template <int DMAX>
+__device__ __forceinline__ double v2_solve_cols(const double *rec, const double (&x)[DMAX]) {
+  const double *mu = rec + AMX_REC_HEAD, *rd = mu + DMAX, *T = rd + DMAX;
+  double v[DMAX];
+#pragma unroll
+  for (int i = 0; i < DMAX; i++) v[i] = x[i] - mu[i];
+  double q = 0.0;
+#pragma unroll
+  for (int j = 0; j < DMAX; j++) {
+    const double r = v[j] * rd[j];
+    q = fma(r, r, q);
+#pragma unroll
+    for (int i = j + 1; i < DMAX; i++) v[i] = fma(-T[AMX_TRI(i, j)], r, v[i]);
+  }
+  return q;
+}
+
+// B-phase of one sample for the warp that owns the entries e = WQ (mod 4) of (S2 | S1 | T): S2 is the packed lower
+// triangle (row-major) of sum w dx dx^T, S1 = sum w dx, T_l = sum E_il * inv.  dxs: the stage's coordinate rows, already
+// shifted by the pivot; Es: its density rows.  (DMAX is the dimension itself.)
 template <int DMAX, int WQ>
-__device__ __forceinline__ void v2_moments(double (&acc)[V2Cfg<DMAX>::NB], const double *dxs, double w, int s, int d) {
-  constexpr int TRI = V2Cfg<DMAX>::TRI;
+__device__ __forceinline__ void v2_bsample(double (&acc)[V2Cfg<DMAX>::NB], const double *dxs, const double *Es, double w,
+                                           double inv, int s, int d, int L) {
+  using CF = V2Cfg<DMAX>;
   double dx[DMAX];
 #pragma unroll
-  for (int j = 0; j < DMAX; j++) dx[j] = (j < d) ? dxs[j * kV2TS + s] : 0.0;
+  for (int j = 0; j < DMAX; j++) dx[j] = dxs[j * kV2TS + s];
   int e = 0;
 #pragma unroll
   for (int j = 0; j < DMAX; j++) {
@@ -110,16 +182,29 @@ __device__ __forceinline__ void v2_moments(double (&acc)[V2Cfg<DMAX>::NB], const
 #pragma unroll
     for (int k = 0; k <= j; k++, e++)
       if ((e & 3) == WQ) acc[e >> 2] = fma(wd, dx[k], acc[e >> 2]);
-    if (((TRI + j) & 3) == WQ) acc[(TRI + j) >> 2] += wd;
+    if (((CF::TRI + j) & 3) == WQ) acc[(CF::TRI + j) >> 2] += wd;
   }
+#pragma unroll
+  for (int i = 0; i < kEmLmax / 4; i++)
+    if (4 * i + WQ < L) acc[CF::NBM + i] = fma(Es[(4 * i + WQ) * kV2TS + s], inv, acc[CF::NBM + i]);
 }
 template <int DMAX, int WQ>
-__device__ __forceinline__ void v2_bphase(double (&acc)[V2Cfg<DMAX>::NB], const double *dxs, const double *ws, int lane, int d) {
+__device__ __forceinline__ void v2_bphase(double (&acc)[V2Cfg<DMAX>::NB], const double *dxs, const double *Es, const double *Enx,
+                                          double lam_nx, const double *winv, int lane, int d, int L) {
 #pragma unroll 1
   for (int q = 0; q < kV2TS / 32; q++) {
     const int s = lane + 32 * q;
-    v2_moments<DMAX, WQ>(acc, dxs, ws[s], s, d);
+    const double inv = winv[s];
+    v2_bsample<DMAX, WQ>(acc, dxs, Es, (lam_nx * Enx[s]) * inv, inv, s, d, L);
   }
+}
+template <int DMAX>
+__device__ __forceinline__ void v2_bphase_any(double (&acc)[V2Cfg<DMAX>::NB], int wq, const double *dxs, const double *Es,
+                                              const double *Enx, double lam_nx, const double *winv, int lane, int d, int L) {
+  if (wq == 0) v2_bphase<DMAX, 0>(acc, dxs, Es, Enx, lam_nx, winv, lane, d, L);
+  else if (wq == 1) v2_bphase<DMAX, 1>(acc, dxs, Es, Enx, lam_nx, winv, lane, d, L);
+  else if (wq == 2) v2_bphase<DMAX, 2>(acc, dxs, Es, Enx, lam_nx, winv, lane, d, L);
+  else v2_bphase<DMAX, 3>(acc, dxs, Es, Enx, lam_nx, winv, lane, d, L);
 }
 
 // in-place removal of component `gone` from the CTA's mixture (:823-836, :908-921)
@@ -368,14 +453,18 @@ __device__ void v2_leader(const EmArgs &a, EmCtrl *c, bool writer, int pass, con
 template <int DMAX, int NTEAM>
 __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2Args v) {
   using CF = V2Cfg<DMAX>;
-  constexpr int TRI = CF::TRI, NB = CF::NB;
+  constexpr int TRI = CF::TRI, NB = CF::NB, NE4 = CF::NE4;
   constexpr int NCONS = NTEAM * 128;
   constexpr int kMaxStages = 8;
   extern __shared__ __align__(128) double smem[];
   __shared__ __align__(8) uint64_t s_full[kMaxStages];
-  __shared__ int s_flag;
+  __shared__ volatile unsigned s_gen[kMaxStages];
+  __shared__ int s_flag, s_nrun;
+  __shared__ int s_run[2 * kEmLmax];
 
-  const int d = a.d, Lmax = a.Lmax, tri = d * (d + 1) / 2;
+  constexpr int d = DMAX;  // one instantiation per dimension: no per-coordinate predicates anywhere
+  const int Lmax = a.Lmax;
+  constexpr int tri = d * (d + 1) / 2;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int team = warp >> 2, wq = warp & 3, tt = t & 127;
   const long n = a.n, np = a.npad;
@@ -385,7 +474,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
   EmCtrl *ctrl = a.ctrl;
 
   // shared memory: [region0: ring, aliased by the end-of-pass reduction scratch][mu][B][rec][tot][part][LeaderS]
-  const int stage_doubles = (d + Lmax + 1) * kV2TS;  // rows: x (d) | E (Lmax, component order) | w_next
+  const int stage_doubles = (d + Lmax + 1) * kV2TS;  // rows: x (d) | E (Lmax, component order) | inv (1/sum, or 1)
   double *ring = smem;
   double *s_mu = smem + v.region0_doubles;           // [Lmax][d]
   double *s_B = s_mu + Lmax * d;                     // [Lmax][tri]
@@ -396,7 +485,10 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
   const int NS = v.ns;
 
   if (t == 0) {
-    for (int q = 0; q < NS; q++) mbar_init(&s_full[q], 1);
+    for (int q = 0; q < NS; q++) {
+      mbar_init(&s_full[q], 1);
+      s_gen[q] = 0u;
+    }
     memset(&S, 0, sizeof(S));
   }
   for (int q = t; q < kV2NV; q += blockDim.x) s_part[q] = 0.0;
@@ -418,13 +510,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       {
         for (long i = (long)blockIdx.x * NCONS + t; i < n; i += (long)G * NCONS) {
 #pragma unroll
-          for (int j = 0; j < DMAX; j++)
-            if (j < d) {
-              const double xv = a.x[i * d + j];
-              __stcg(a.xT + (size_t)j * np + i, xv);
-              acc[j] += xv;
-              acc[DMAX + j] = fma(xv, xv, acc[DMAX + j]);
-            }
+          for (int j = 0; j < DMAX; j++) {
+            const double xv = a.x[i * d + j];
+            __stcg(a.xT + v2_x_at(i, j, d), xv);
+            acc[j] += xv;
+            acc[DMAX + j] = fma(xv, xv, acc[DMAX + j]);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 2 * DMAX; j++) {
@@ -447,23 +538,39 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       const bool dens_all = (pass == kPassRefresh0);  // first E-step: every density is formed here, unguarded weights
       const bool dens = (pass == kPassDensRefresh);
       const int ntile_cta = (int)((ntiles - (long)blockIdx.x + G - 1) / G);  // tiles b, b+G, ... of this CTA
-      const int rows = dens_all ? d : d + L - (dens ? 1 : 0);
-      // one warp's lanes issue the row copies of tile `it` of this CTA into stage (seq_base + it) % NS
+      // Runs of consecutive live slots (the slot list is increasing: annihilation removes entries, never reorders):
+      // run r covers components [s_run[2r], s_run[2r] + s_run[2r+1]).  The refreshed component's stale row is copied
+      // with its run and overwritten in the stage (1 KB per tile, cheaper than splitting the run).
+      if (t == 0) {
+        int nr = 0;
+        for (int l = 0; l < L && !dens_all; l++) {
+          if (l == 0 || S.slot[l] != S.slot[l - 1] + 1) {
+            s_run[2 * nr] = l;
+            s_run[2 * nr + 1] = 0;
+            nr++;
+          }
+          s_run[2 * (nr - 1) + 1]++;
+        }
+        s_nrun = nr;
+      }
+      __syncthreads();
+      const int nrun = s_nrun;
+      const int rows = dens_all ? d : d + L;
+      // lane 0 copies the coordinates of tile `it` of this CTA into stage (seq_base + it) % NS, lane r + 1 run r
       auto fetch = [&](int it) {
         const unsigned long long seq = seq_base + (unsigned long long)it;
         const int st = (int)(seq % (unsigned)NS);
         double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS;
         const long tl = (long)blockIdx.x + (long)it * G;
-        if (lane == 0) mbar_expect_tx(&s_full[st], (uint32_t)(rows * kV2TS * 8));
+        if (lane == 0) {
+          s_gen[st] = (unsigned)(seq / (unsigned)NS) + 1u;  // fills issued for this stage
+          mbar_expect_tx(&s_full[st], (uint32_t)(rows * kV2TS * 8));
+          tma_load_row(xs, a.xT + (size_t)tl * d * kV2TS, (uint32_t)(d * kV2TS * 8), &s_full[st]);
+        }
         __syncwarp();
-        for (int q = lane; q < d + (dens_all ? 0 : L); q += 32) {
-          if (q < d) {
-            tma_load_row(xs + q * kV2TS, a.xT + (size_t)q * np + tl * kV2TS, kV2TS * 8, &s_full[st]);
-          } else {
-            const int l = q - d;
-            if (!(dens && l == cc))
-              tma_load_row(Es + l * kV2TS, a.E + (size_t)S.slot[l] * np + tl * kV2TS, kV2TS * 8, &s_full[st]);
-          }
+        if (lane >= 1 && lane <= nrun) {
+          const int l0 = s_run[2 * (lane - 1)], len = s_run[2 * (lane - 1) + 1];
+          tma_load_row(Es + l0 * kV2TS, a.E + ((size_t)tl * Lmax + S.slot[l0]) * kV2TS, (uint32_t)(len * kV2TS * 8), &s_full[st]);
         }
       };
       // prologue: the ring is idle (end-of-pass barrier): warp 0 fills it
@@ -471,121 +578,110 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       if (warp == 0)
         for (int it = 0; it < NS && it < ntile_cta; it++) fetch(it);
       {
-        double accT[kEmLmax];  // T_l = sum_i E_il / sum_i  (column sum of the responsibilities = lam_l T_l)
-        double accB[NB];
+        double acc[NB];  // this thread's share of (S2 | S1 | T): entries e = wq (mod 4), over the samples it walks
 #pragma unroll
-        for (int l = 0; l < kEmLmax; l++) accT[l] = 0.0;
-#pragma unroll
-        for (int q = 0; q < NB; q++) accB[q] = 0.0;
+        for (int q = 0; q < NB; q++) acc[q] = 0.0;
         double ll = 0.0, nfb = 0.0;
         const int cslot = dens ? S.slot[cc] : 0;
         const double *lam = S.lam;
         for (int it = team; it < ntile_cta; it += NTEAM) {
           const unsigned long long seq = seq_base + (unsigned long long)it;
           const int st = (int)(seq % (unsigned)NS);
-          double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS, *ws = Es + Lmax * kV2TS;
+          double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS, *winv = Es + Lmax * kV2TS;
           const long tl = (long)blockIdx.x + (long)it * G;
           const long i = tl * kV2TS + tt;
           const bool valid = i < n;
-          mbar_wait_wd(&s_full[st], (uint32_t)((seq / NS) & 1ull));
+          // try_wait.parity can only tell the barrier's current phase from the one before it, so a team that runs
+          // ahead must not look at the barrier before this fill has been issued (the stage's previous fill is then
+          // complete and consumed: the barrier is in this fill's phase or just past it)
+          {
+            const unsigned fill = (unsigned)(seq / (unsigned)NS);
+            if (lane == 0) {
+              const long long t0 = clock64();
+              while (s_gen[st] <= fill) {
+                __nanosleep(40);
+                if (clock64() - t0 > 20000000000LL) __trap();
+              }
+            }
+            __syncwarp();
+            mbar_wait_wd(&s_full[st], fill & 1u);
+          }
           // ---- A-phase: thread tt owns sample tt of the stage
           double *Ecol = Es + tt;
           double xv[DMAX];
 #pragma unroll
-          for (int j = 0; j < DMAX; j++) xv[j] = (j < d) ? xs[j * kV2TS + tt] : 0.0;
+          for (int j = 0; j < DMAX; j++) xv[j] = xs[j * kV2TS + tt];
           if (dens_all) {
             const double rd = s_rec[AMX_REC_HEAD + d], c1 = s_rec[3];  // all start factors are sqrt(s2) I
             for (int l = 0; l < L; l++) {
               const double *mu = s_mu + l * d;
               double q = 0.0;
 #pragma unroll
-              for (int j = 0; j < DMAX; j++)
-                if (j < d) {
-                  const double r = (xv[j] - mu[j]) * rd;
-                  q = fma(r, r, q);
-                }
+              for (int j = 0; j < DMAX; j++) {
+                const double r = (xv[j] - mu[j]) * rd;
+                q = fma(r, r, q);
+              }
               const double e = exp(fma(-0.5, q, c1));
               Ecol[l * kV2TS] = e;
-              if (valid) __stcg(a.E + (size_t)S.slot[l] * np + i, e);
+              if (valid) __stcg(a.E + v2_e_at(i, S.slot[l], Lmax), e);
             }
           } else if (dens) {
-            double r[DMAX];
-            const double enew = exp(fma(-0.5, solve_lower<DMAX, true>(s_rec, d, xv, r), s_rec[3]));
+            const double enew = exp(fma(-0.5, v2_solve_cols<DMAX>(s_rec, xv), s_rec[3]));
             Ecol[cc * kV2TS] = enew;
-            if (valid) __stcg(a.E + (size_t)cslot * np + i, enew);
+            if (valid) __stcg(a.E + v2_e_at(i, cslot, Lmax), enew);
           }
           // sum_l lam_l E_il in component order (as the reference adds them)
-          double sum = 0.0;
-          for (int l = 0; l < L; l++) sum = fma(lam[l], Ecol[l * kV2TS], sum);
-          double wn = 0.0;
-          if (!valid) {
-            // padding sample: no weight anywhere
+          double sum;
+          {
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;  // four chains: the sum moves by rounding only
+            int l = 0;
+            for (; l + 4 <= L; l += 4) {
+              p0 = fma(lam[l], Ecol[l * kV2TS], p0);
+              p1 = fma(lam[l + 1], Ecol[(l + 1) * kV2TS], p1);
+              p2 = fma(lam[l + 2], Ecol[(l + 2) * kV2TS], p2);
+              p3 = fma(lam[l + 3], Ecol[(l + 3) * kV2TS], p3);
+            }
+            for (; l < L; l++) p0 = fma(lam[l], Ecol[l * kV2TS], p0);
+            sum = (p0 + p1) + (p2 + p3);
+          }
+          // The responsibilities enter the column sums as T_l += E_il * inv (B-phase).  The common case sets
+          // inv = 1 / sum; every other case (first E-step, densities near the subnormal range, NaN) first rewrites the
+          // sample's column of the stage to w_il / lam_l and uses inv = 1.
+          double wn = 0.0, inv = 1.0;
+          if (!valid) {  // padding sample: no weight anywhere (its cache column may hold anything)
+            for (int l = 0; l < L; l++) Ecol[l * kV2TS] = 0.0;
           } else if (dens_all) {
             // First E-step: w = lam * pdf / sum with no look at the sum, as the reference does (:737-745); 0/0 = NaN
             // poisons the column sums and components are annihilated until a guarded refresh clears it.
-#pragma unroll
-            for (int l = 0; l < kEmLmax; l++)
-              if (l < L) {
-                const double w = (lam[l] * Ecol[l * kV2TS]) / sum;
-                accT[l] += w / lam[l];
-                if (l == nx) wn = w;
-              }
-          } else if (sum >= 1e-280) {  // the reference's guard (:855-866) holds, and 1/sum is safe
-            const double inv = 1.0 / sum;
-            ll += log(sum);
-#pragma unroll
-            for (int l = 0; l < kEmLmax; l++)
-              if (l < L) accT[l] = fma(Ecol[l * kV2TS], inv, accT[l]);
-            wn = (lam[nx] * Ecol[nx * kV2TS]) * inv;
-          } else if (sum < 1e-280) {
-            // Every component puts this sample below exp(-644): cached densities near the subnormal range, where
-            // lam * exp(lpd) no longer tracks the reference's exp(log(lam) + lpd) (nor can 1/sum be formed).
-            // Redo the sample the reference's way from the components' parameters (:849-866).
-            double s2 = 0.0;
             for (int l = 0; l < L; l++) {
-              const double wl = exp(log(lam[l]) + v2_lnormprob_slow(s_mu + l * d, s_B + l * tri, d, xs + tt));
-              Ecol[l * kV2TS] = wl;
-              s2 += wl;
+              const double w = (lam[l] * Ecol[l * kV2TS]) / sum;
+              Ecol[l * kV2TS] = w / lam[l];
+              if (l == nx) wn = w;
             }
-            if (s2 > 0) {
-              ll += log(s2);
-#pragma unroll
-              for (int l = 0; l < kEmLmax; l++)
-                if (l < L) {
-                  const double w = Ecol[l * kV2TS] / s2;
-                  accT[l] += (lam[l] > 0.0) ? w / lam[l] : 0.0;
-                  if (l == nx) wn = w;
-                }
-            } else {
-              nfb += 1.0;
-              const double w = 1.0 / L;
-#pragma unroll
-              for (int l = 0; l < kEmLmax; l++)
-                if (l < L) accT[l] += (lam[l] > 0.0) ? w / lam[l] : 0.0;
-              wn = (L > 0) ? w : 0.0;
-            }
-          } else {  // NaN sum: the reference's `sum > 0` fails -> uniform responsibilities and the -500 penalty
-            nfb += 1.0;
-            const double w = 1.0 / L;
-#pragma unroll
-            for (int l = 0; l < kEmLmax; l++)
-              if (l < L) accT[l] += (lam[l] > 0.0) ? w / lam[l] : 0.0;
-            wn = (L > 0) ? w : 0.0;
+          } else if (sum >= 1e-280) {  // the reference's guard (:855-866) holds, and 1/sum is safe
+            inv = 1.0 / sum;
+            ll += log(sum);
+            wn = (lam[nx] * Ecol[nx * kV2TS]) * inv;
+          } else {
+            wn = v2_slow_sample(lam, s_mu, s_B, d, tri, L, nx, sum, xs + tt, Ecol, &ll, &nfb);
           }
-          ws[tt] = wn;
+          winv[tt] = inv;
+          (void)wn;  // the B-phase forms w_next = lam_nx E_i,nx inv itself (in the rewritten cases that is w to an ulp)
           // shift by the pivot (current mean of the next component): the rows become dx = x - pivot
           {
             const double *piv = s_mu + nx * d;
 #pragma unroll
-            for (int j = 0; j < DMAX; j++)
-              if (j < d) xs[j * kV2TS + tt] = valid ? xv[j] - piv[j] : 0.0;
+            for (int j = 0; j < DMAX; j++) {
+              const double v0 = xv[j] - piv[j];
+              xs[j * kV2TS + tt] = valid ? v0 : 0.0;
+            }
           }
           named_bar(1 + team, 128);
           // ---- B-phase: warp wq owns the entries e = wq (mod 4) of (S2 | S1) over all 128 samples
-          if (wq == 0) v2_bphase<DMAX, 0>(accB, xs, ws, lane, d);
-          else if (wq == 1) v2_bphase<DMAX, 1>(accB, xs, ws, lane, d);
-          else if (wq == 2) v2_bphase<DMAX, 2>(accB, xs, ws, lane, d);
-          else v2_bphase<DMAX, 3>(accB, xs, ws, lane, d);
+          {
+            const double lam_nx = (nx < L) ? lam[nx] : 0.0;  // empty mixture: no weight
+            v2_bphase_any<DMAX>(acc, wq, xs, Es, Es + nx * kV2TS, lam_nx, winv, lane, d, L);
+          }
           // the stage is free once all four warps are through; the team refills it with the tile NS places ahead
           fence_proxy_async();
           named_bar(1 + team, 128);
@@ -595,42 +691,45 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
         // Lanes are first folded four to one by shuffles; the 8 x 4 NTEAM group sums per value go through the
         // (now idle) ring memory.
         named_bar(8, NCONS);  // every stage has been consumed
-        constexpr int NG = NCONS / 4;  // group writers
-        double *scrA = ring;                      // [kEmLmax + 2][NG]
-        double *scrB = ring + (kEmLmax + 2) * NG;  // [4 NB][NG / 4]: entry e = 4 i + wq, writers of the same wq
-        const int grp = t >> 2;
-#pragma unroll
-        for (int l = 0; l < kEmLmax + 2; l++) {
-          double r = (l < kEmLmax) ? accT[l < kEmLmax ? l : 0] : (l == kEmLmax ? ll : nfb);
-          r += __shfl_xor_sync(0xffffffffu, r, 1);
-          r += __shfl_xor_sync(0xffffffffu, r, 2);
-          if ((lane & 3) == 0) scrA[l * NG + grp] = r;
-        }
+        constexpr int NW = NTEAM * 8;              // writers per entry: 8 four-lane groups of the owning warp of each team
+        double *scr = ring;                        // [4 NB][NW]: entry e = 4 q + wq
+        double *scr2 = ring + 4 * NB * NW;         // [2][4 NTEAM] log-likelihood and fallback count per warp
 #pragma unroll
         for (int q = 0; q < NB; q++) {
-          double r = accB[q];
+          double r = acc[q];
           r += __shfl_xor_sync(0xffffffffu, r, 1);
           r += __shfl_xor_sync(0xffffffffu, r, 2);
-          if ((lane & 3) == 0) scrB[(4 * q + wq) * (NG / 4) + team * 8 + (lane >> 2)] = r;
+          if ((lane & 3) == 0) scr[(4 * q + wq) * NW + team * 8 + (lane >> 2)] = r;
+        }
+        {
+          const double r0 = warp_sum(ll), r1 = warp_sum(nfb);
+          if (lane == 0) {
+            scr2[warp] = r0;
+            scr2[4 * NTEAM + warp] = r1;
+          }
         }
         named_bar(8, NCONS);
-        for (int l = warp; l < kEmLmax + 2; l += 4 * NTEAM) {
-          double r = 0.0;
-          for (int g = lane; g < NG; g += 32) r += scrA[l * NG + g];
+        for (int e = warp; e < CF::NEALL; e += 4 * NTEAM) {
+          double r = (lane < NW) ? scr[e * NW + lane] : 0.0;
           r = warp_sum(r);
-          if (lane == 0) s_part[l] = r;
-        }
-        for (int e = warp; e < TRI + DMAX; e += 4 * NTEAM) {
-          double r = (lane < NG / 4) ? scrB[e * (NG / 4) + lane] : 0.0;
-          r = warp_sum(r);
-          // entry e of the DMAX-packed (S2 | S1) -> position in the partial row: S1 first, then the d-packed triangle
+          // entry e of the DMAX-packed (S2 | S1 | pad | T) -> position in the partial row [T | ll | nfb | S1 | S2 d-packed]
           // (rows j < d of the packed triangle are its first tri(d) entries in either packing)
           if (lane == 0) {
-            if (e >= TRI) {
+            if (e >= NE4) s_part[e - NE4] = r;
+            else if (e >= TRI) {
               if (e - TRI < d) s_part[kEmLmax + 2 + (e - TRI)] = r;
             } else if (e < tri) {
               s_part[kEmLmax + 2 + d + e] = r;
             }
+          }
+        }
+        if (warp == 0) {
+          double r0 = (lane < 4 * NTEAM) ? scr2[lane] : 0.0, r1 = (lane < 4 * NTEAM) ? scr2[4 * NTEAM + lane] : 0.0;
+          r0 = warp_sum(r0);
+          r1 = warp_sum(r1);
+          if (lane == 0) {
+            s_part[kEmLmax] = r0;
+            s_part[kEmLmax + 1] = r1;
           }
         }
       }
@@ -656,19 +755,36 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     if (s_flag) {
       // last CTA of this GPU: sum the GPU's partial rows (lanes over consecutive CTAs of one value: coalesced;
       // fixed order), then post the row to every GPU's inbox and raise this GPU's flag there
-      for (int q = warp; q < nv; q += (int)(blockDim.x >> 5)) {
-        const double *src = v.part + (size_t)q * G;
-        double r = 0.0;
-        for (int b = lane; b < G; b += 32) r += ld_cg(src + b);
-        r = warp_sum(r);
-        if (lane == 0) s_tot[q] = r;
+      {  // every load of this warp's values is issued before the first add: one L2 round trip, not one per value
+        constexpr int NWARP = 4 * NTEAM, KV = (kV2NV + NWARP - 1) / NWARP, KB = 5;  // KB * 32 >= 148 CTAs
+        double vv[KV][KB];
+#pragma unroll
+        for (int k = 0; k < KV; k++) {
+          const int q = warp + NWARP * k;
+#pragma unroll
+          for (int m = 0; m < KB; m++) {
+            const int b = lane + 32 * m;
+            vv[k][m] = (q < nv && b < G) ? ld_cg(v.part + (size_t)q * G + b) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KV; k++) {
+          const int q = warp + NWARP * k;
+          double r = 0.0;
+#pragma unroll
+          for (int m = 0; m < KB; m++) r += vv[k][m];
+          for (int b = lane + 32 * KB; b < G; b += 32) r += ld_cg(v.part + (size_t)(q < nv ? q : 0) * G + b);  // larger grids
+          r = warp_sum(r);
+          if (lane == 0 && q < nv) s_tot[q] = r;
+        }
       }
       __syncthreads();
       for (int q = t; q < nv * a.ndev; q += blockDim.x) {
         const int g = q / nv, k = q - g * nv;
         v.sync[g]->inbox[par][a.rank][k] = s_tot[k];
       }
-      __threadfence_system();
+      if (a.ndev > 1) __threadfence_system();
+      else __threadfence();
       __syncthreads();
       if (t < a.ndev) st_release_sys(&v.sync[t]->flag[a.rank][0], epoch + 1u);
     }
@@ -702,6 +818,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     v2_leader<DMAX>(a, ctrl, writer, pass, s_tot, S, s_mu, s_B, s_rec);
     const long long tk3 = clock64();
     dbg_pass += tk1 - tk0;
+    if (v.debug && t == 0) me->dbg_cta[blockIdx.x < 160 ? blockIdx.x : 159] = dbg_pass;
     dbg_bar += tk2 - tk1;
     dbg_lead += tk3 - tk2;
     pass = S.pass;
@@ -729,9 +846,9 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     const int L = S.L;
     for (long i = (long)blockIdx.x * blockDim.x + t; i < n; i += (long)G * blockDim.x) {
       double sum = 0.0;
-      for (int l = 0; l < L; l++) sum += S.lam[l] * __ldcg(a.E + (size_t)S.slot[l] * np + i);
+      for (int l = 0; l < L; l++) sum += S.lam[l] * __ldcg(a.E + v2_e_at(i, S.slot[l], Lmax));
       for (int l = 0; l < L; l++) {
-        const double e = __ldcg(a.E + (size_t)S.slot[l] * np + i);
+        const double e = __ldcg(a.E + v2_e_at(i, S.slot[l], Lmax));
         a.w_out[(size_t)i * a.Lmax + l] = (sum > 0) ? S.lam[l] * e / sum : 1.0 / L;
       }
     }
@@ -745,5 +862,5 @@ constexpr size_t v2_fixed_doubles(int d, int Lmax) {
 }
 template <int DMAX, int NTEAM>
 constexpr size_t v2_scratch_doubles() {
-  return (size_t)(kEmLmax + 2) * (NTEAM * 32) + (size_t)4 * V2Cfg<DMAX>::NB * (NTEAM * 8) + 64;
+  return (size_t)4 * V2Cfg<DMAX>::NB * (NTEAM * 8) + 8 * NTEAM + 64;
 }

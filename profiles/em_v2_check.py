@@ -24,7 +24,7 @@ if mode == "small":
         x, _ = W.c5_em_samples(n=n, d=d, G=G, seed=7 + d)
         idx, _ = amx.em_draw_init(n, Lmax, W.splitmix_uniforms_fast(5, 4096))
         a = fit(x, idx, Lmax, maxit, False)
-        for teams in (3, 2):
+        for teams in (3,):
             b = fit(x, idx, Lmax, maxit, True, AMX_EM_TEAMS=teams)
             same = np.array_equal(a["trace_L"], b["trace_L"]) and np.array_equal(a["trace_ann"], b["trace_ann"])
             print(f"n={n} d={d} Lmax={Lmax} teams={teams}: iters {a['iters']}/{b['iters']} trace same={same} "
@@ -35,11 +35,15 @@ else:
     x, _ = W.c5_em_samples(n=n, d=d, G=6, seed=2025)
     idx, _ = amx.em_draw_init(n, Lmax, W.splitmix_uniforms_fast(2025, 4096))
     maxit = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    if len(sys.argv) > 3:  # profile mode: one second-generation fit only
+        b = fit(x, idx, Lmax, maxit, True, AMX_EM_TEAMS=int(sys.argv[3]))
+        print(f"v2: {b['kernel_ms']:.2f} ms, {b['comp_steps']} steps")
+        sys.exit(0)
     os.environ["AMX_EM_DEBUG"] = "1"
     a = fit(x, idx, Lmax, maxit, False)
     print(f"v1: {a['kernel_ms']:.2f} ms, {a['comp_steps']} steps, {1e3*a['kernel_ms']/a['comp_steps']:.1f} us/step", flush=True)
-    for teams in (3, 2):
-        for ns in (8, 3, 2):
+    for teams in (3,):
+        for ns in (8,):
             for rep in range(2):
                 b = fit(x, idx, Lmax, maxit, True, AMX_EM_TEAMS=teams, AMX_EM_STAGES=ns)
             same = np.array_equal(a["trace_L"], b["trace_L"])
