@@ -1849,8 +1849,8 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
       }
     }
     if (getenv("AMX_EM_DEBUG") && use_v2)
-      fprintf(stderr, "[em2 dbg] %d GPU(s), %d teams, %d stages, %zu B smem; CTA 0 of GPU 0, cycles: data passes %lld | exchange %lld | sequential section %lld (%ld component steps)\n",
-              ndev, nteam, plan.ns, plan.smem, c->dbg[0], c->dbg[1], c->dbg[3], c->comp_steps);
+      fprintf(stderr, "[em2 dbg] %d GPU(s), %d teams, %d stages, %zu B smem; CTA 0 of GPU 0, cycles: data passes %lld | exchange %lld (post row + arrive %lld, wait for totals %lld) | sequential section %lld (%ld component steps)\n",
+              ndev, nteam, plan.ns, plan.smem, c->dbg[0], c->dbg[1], c->dbg[4], c->dbg[5], c->dbg[3], c->comp_steps);
     else if (getenv("AMX_EM_DEBUG"))
       fprintf(stderr, "[em dbg] %d GPU(s), cycles on GPU 0: block0 data pass %lld | leader: arrive-skew+reduce %lld logic %lld | block0 wait %lld reload %lld (phases ~%ld) | scatter passes %lld refresh passes %lld\n",
               ndev, c->dbg[0], c->dbg[1], c->dbg[3], c->dbg[4], c->dbg[5], 2 * c->comp_steps, c->dbg[6], c->dbg[7]);

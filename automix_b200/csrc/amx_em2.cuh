@@ -111,10 +111,12 @@ __device__ __noinline__ double v2_lnormprob_slow(const double *mu, const double 
 
 // A sample whose total density is below 1e-280 (or NaN), redone the reference's way (:849-866): every component puts
 // it below exp(-644), the cached densities are near the subnormal range where lam * exp(lpd) no longer tracks the
-// reference's exp(log(lam) + lpd) and 1/sum cannot be formed.  Leaves w_l / lam_l in the sample's column of the stage
-// (the caller accumulates it with multiplier 1), returns the responsibility of component nx.
+// reference's exp(log(lam) + lpd) and 1/sum cannot be formed.  Leaves w_l / lam_l (or w_l itself in a `direct` pass, see
+// the kernel) in the sample's column of the stage (the caller accumulates it with multiplier 1), returns the
+// responsibility of component nx.
 __device__ __noinline__ double v2_slow_sample(const double *lam, const double *s_mu, const double *s_B, int d, int tri, int L,
-                                              int nx, double sum, const double *xcol, double *Ecol, double *ll, double *nfb) {
+                                              int nx, double sum, bool direct, const double *xcol, double *Ecol, double *ll,
+                                              double *nfb) {
   double wn = 0.0;
   bool uniform = !(sum < 1e-280);  // NaN sum: the reference's `sum > 0` fails -> uniform responsibilities, -500 penalty
   if (!uniform) {
@@ -128,7 +130,7 @@ __device__ __noinline__ double v2_slow_sample(const double *lam, const double *s
       *ll += log(s2);
       for (int l = 0; l < L; l++) {
         const double w = Ecol[l * kV2TS] / s2;
-        Ecol[l * kV2TS] = (lam[l] > 0.0) ? w / lam[l] : 0.0;
+        Ecol[l * kV2TS] = direct ? w : w / lam[l];
         if (l == nx) wn = w;
       }
     } else {
@@ -138,7 +140,7 @@ __device__ __noinline__ double v2_slow_sample(const double *lam, const double *s
   if (uniform) {
     *nfb += 1.0;
     const double w = 1.0 / L;
-    for (int l = 0; l < L; l++) Ecol[l * kV2TS] = (lam[l] > 0.0) ? w / lam[l] : 0.0;
+    for (int l = 0; l < L; l++) Ecol[l * kV2TS] = direct ? w : w / lam[l];
     wn = (L > 0) ? w : 0.0;
   }
   return wn;
@@ -207,29 +209,49 @@ __device__ __forceinline__ void v2_bphase_any(double (&acc)[V2Cfg<DMAX>::NB], in
   else v2_bphase<DMAX, 3>(acc, dxs, Es, Enx, lam_nx, winv, lane, d, L);
 }
 
-// in-place removal of component `gone` from the CTA's mixture (:823-836, :908-921)
+// The sequential section, run by every CTA on its own copy of the state (see the header) -- by ONE WARP of it: nothing
+// in it is wider than 32 (components) except the d(d+1)/2 <= 78 entries of a factor, and a warp-synchronous section
+// has no CTA barriers (the block-cooperative form of the first generation spent most of its ~14k cycles in some
+// fourteen of them).  Scalars that every lane needs (sums in the reference's index order) are formed by every lane
+// redundantly -- same operations, same result -- instead of being broadcast.  Mirrors em_leader_block branch for
+// branch; `writer` (GPU 0, CTA 0) also records what the host reads back: traces and the best mixture.
 template <int DMAX>
-__device__ __forceinline__ void v2_drop(LeaderS<DMAX> &S, double *s_mu, double *s_B, int d, int gone) {
-  const int t = threadIdx.x, nt = blockDim.x, tri = d * (d + 1) / 2, L = S.L;
-  for (int q = t; q < tri; q += nt)
+__device__ __forceinline__ void v2w_renorm(LeaderS<DMAX> &S, int lane) {  // lam /= sum(lam), sum in index order (:785-792)
+  double sum = 0.0;
+  for (int l = 0; l < S.L; l++) sum += S.lam[l];
+  __syncwarp();
+  if (lane < S.L) S.lam[lane] /= sum;
+  __syncwarp();
+}
+template <int DMAX>
+__device__ __forceinline__ double v2w_cost(const LeaderS<DMAX> &S, int lane, long n, int nparams, double loglik) {  // :870-876
+  const double mine = (lane < S.L) ? log((double)n * S.lam[lane] / 12.0) : 0.0;
+  double sum = 0.0;
+  for (int l = 0; l < S.L; l++) sum += __shfl_sync(0xffffffffu, mine, l);
+  return (nparams / 2.0) * sum + (S.L / 2.0) * log((double)n / 12.0) + S.L * (nparams + 1) / 2.0 - loglik;
+}
+template <int DMAX>
+__device__ __forceinline__ void v2w_drop(LeaderS<DMAX> &S, double *s_mu, double *s_B, int lane, int gone) {  // :823-836, :908-921
+  constexpr int d = DMAX, tri = d * (d + 1) / 2;
+  const int L = S.L;
+  for (int q = lane; q < tri; q += 32)
     for (int l = gone; l < L - 1; l++) s_B[l * tri + q] = s_B[(l + 1) * tri + q];
-  if (t < d)
-    for (int l = gone; l < L - 1; l++) s_mu[l * d + t] = s_mu[(l + 1) * d + t];
-  __syncthreads();
-  if (t == 0) {
+  if (lane < d)
+    for (int l = gone; l < L - 1; l++) s_mu[l * d + lane] = s_mu[(l + 1) * d + lane];
+  __syncwarp();
+  if (lane == 0) {
     for (int l = gone; l < L - 1; l++) {
       S.lam[l] = S.lam[l + 1];
       S.slot[l] = S.slot[l + 1];
     }
     S.L = L - 1;
   }
-  __syncthreads();
+  __syncwarp();
 }
-
 template <int DMAX>
-__device__ __forceinline__ void v2_make_rec(LeaderS<DMAX> &S, const double *s_mu, double *s_rec, int d, int l) {
-  const int t = threadIdx.x, tri = d * (d + 1) / 2;
-  if (t == 0) {
+__device__ __forceinline__ void v2w_make_rec(LeaderS<DMAX> &S, const double *s_mu, double *s_rec, int lane, int l) {
+  constexpr int d = DMAX, tri = d * (d + 1) / 2;
+  if (lane == 0) {
     double prod = 1.0;
     for (int i = 0; i < d; i++) prod *= S.Bc[AMX_TRI(i, i)];
     const double ld = log(prod);
@@ -238,35 +260,36 @@ __device__ __forceinline__ void v2_make_rec(LeaderS<DMAX> &S, const double *s_mu
     s_rec[2] = ld;
     s_rec[3] = -(d / 2.0) * log(2.0 * 3.14159265358979323846) - ld;
   }
-  if (t < d) {
-    s_rec[AMX_REC_HEAD + t] = s_mu[l * d + t];
-    s_rec[AMX_REC_HEAD + d + t] = 1.0 / S.Bc[AMX_TRI(t, t)];
+  if (lane < d) {
+    s_rec[AMX_REC_HEAD + lane] = s_mu[l * d + lane];
+    s_rec[AMX_REC_HEAD + d + lane] = 1.0 / S.Bc[AMX_TRI(lane, lane)];
   }
-  for (int q = t; q < tri; q += blockDim.x) s_rec[AMX_REC_HEAD + 2 * d + q] = S.Bc[q];
+  for (int q = lane; q < tri; q += 32) s_rec[AMX_REC_HEAD + 2 * d + q] = S.Bc[q];
+  __syncwarp();
 }
 
-// The sequential section, run by every CTA on its own copy of the state (see the header).  Mirrors em_leader_block
-// branch for branch; `writer` (GPU 0, CTA 0) also records what the host reads back: traces and the best mixture.
 template <int DMAX>
-__device__ void v2_leader(const EmArgs &a, EmCtrl *c, bool writer, int pass, const double *s_tot, LeaderS<DMAX> &S,
-                          double *s_mu, double *s_B, double *s_rec) {
-  const int t = threadIdx.x, nt = blockDim.x, d = a.d, tri = d * (d + 1) / 2, nparams = d + tri;
-  if (t == 0) {
-    S.act = kActDone;
-    S.keep = 0;
-    S.drop = -1;
-    S.savebest = 0;
-    S.chol_ok = 1;
-  }
-  __syncthreads();
+__device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass, const double *s_tot, LeaderS<DMAX> &S,
+                               double *s_mu, double *s_B, double *s_rec) {
+  constexpr int d = DMAX, tri = d * (d + 1) / 2, nparams = d + tri;
+  const int lane = threadIdx.x & 31;
   if (pass == kPassInitStats) {
     // :700-723 common isotropic start; s_tot = [sum x_j (d) | sum x_j^2 (d)]
-    if (t == 0) {
-      double s2 = 0.0;
-      const double len = (double)a.n_total;
-      for (int j = 0; j < d; j++) s2 += (s_tot[d + j] - s_tot[j] * s_tot[j] / len) / len;
-      s2 /= (10.0 * d);
-      S.scal = sqrt(s2);
+    double s2 = 0.0;
+    const double len = (double)a.n_total;
+    for (int j = 0; j < d; j++) s2 += (s_tot[d + j] - s_tot[j] * s_tot[j] / len) / len;
+    s2 /= (10.0 * d);
+    const double scal = sqrt(s2);
+    for (int q = lane; q < a.Lmax * d; q += 32) s_mu[q] = ld_cg(a.init_rows + q);
+    for (int q = lane; q < a.Lmax * tri; q += 32) s_B[q] = 0.0;
+    for (int q = lane; q < tri; q += 32) S.Bc[q] = 0.0;
+    S.slot[lane] = lane;
+    S.lam[lane] = (lane < a.Lmax) ? 1.0 / a.Lmax : 0.0;
+    __syncwarp();
+    for (int q = lane; q < a.Lmax * d; q += 32) s_B[(q / d) * tri + AMX_TRI(q % d, q % d)] = scal;
+    if (lane < d) S.Bc[AMX_TRI(lane, lane)] = scal;
+    if (lane == 0) {
+      S.scal = scal;
       if (!(s2 > 0.0)) S.status = AMX_ENUMERIC;
       S.L = a.Lmax;
       S.c = a.Lmax;  // every start density is formed by the first E-step itself
@@ -274,179 +297,157 @@ __device__ void v2_leader(const EmArgs &a, EmCtrl *c, bool writer, int pass, con
       S.iters = 0;
       S.pass = kPassRefresh0;
     }
-    __syncthreads();
-    for (int q = t; q < a.Lmax * d; q += nt) s_mu[q] = ld_cg(a.init_rows + q);
-    for (int q = t; q < a.Lmax * tri; q += nt) s_B[q] = 0.0;
-    __syncthreads();
-    for (int q = t; q < a.Lmax * d; q += nt) s_B[(q / d) * tri + AMX_TRI(q % d, q % d)] = S.scal;
-    if (t < kEmLmax) {
-      S.slot[t] = t;
-      S.lam[t] = (t < a.Lmax) ? 1.0 / a.Lmax : 0.0;
-    }
-    for (int q = t; q < tri; q += nt) S.Bc[q] = 0.0;
-    __syncthreads();
-    if (t < d) S.Bc[AMX_TRI(t, t)] = S.scal;
-    __syncthreads();
-    v2_make_rec<DMAX>(S, s_mu, s_rec, d, 0);
+    __syncwarp();
+    v2w_make_rec<DMAX>(S, s_mu, s_rec, lane, 0);
+    return;
+  }
+  // a refresh finished: s_tot = [T_l (Lmax) | loglik | fallbacks | S1 (d) | S2 (tri)], column sums are lam_l T_l
+  S.colsum[lane] = (lane < S.L) ? (S.keep ? s_tot[lane] : S.lam[lane] * s_tot[lane]) : 0.0;  // S.keep: a `direct` pass
+  if (lane < d) S.S1[lane] = s_tot[kEmLmax + 2 + lane];
+  for (int q = lane; q < tri; q += 32) S.S2[q] = s_tot[kEmLmax + 2 + d + q];
+  const double loglik = s_tot[kEmLmax] - 500.0 * s_tot[kEmLmax + 1];
+  __syncwarp();
+  // every lane carries the scalar state in registers; lane 0 writes it back at the end
+  int L = S.L, cc = S.c, next = S.next, iters = S.iters, natural = S.natural, forced = S.forced, stop = S.stop, status = S.status;
+  int best_L = S.best_L, npass = S.pass, forced_pending = S.forced_pending;
+  long comp_steps = S.comp_steps;
+  double flops = S.flops, cost = S.cost, cost_prev = S.cost_prev, cost_best = S.cost_best;
+  int act;
+  if (iters == 0) {  // initial E-step done: start outer iteration 1
+    iters = 1;
+    natural = forced = 0;
+    cc = 0;
+    act = kActPlan;
+  } else if (forced_pending) {  // refresh after a forced annihilation (:931-958): the cost after it
+    cost = v2w_cost<DMAX>(S, lane, a.n_total, nparams, loglik);
+    forced_pending = 0;
+    act = kActFinishIter;
   } else {
-    // a refresh finished: s_tot = [T_l (Lmax) | loglik | fallbacks | S1 (d) | S2 (tri)], column sums are lam_l T_l
-    if (t < kEmLmax) S.colsum[t] = (t < S.L) ? S.lam[t] * s_tot[t] : 0.0;
-    if (t < d) S.S1[t] = s_tot[kEmLmax + 2 + t];
-    for (int q = t; q < tri; q += nt) S.S2[q] = s_tot[kEmLmax + 2 + d + q];
-    if (t == 0) {
-      S.loglik = s_tot[kEmLmax] - 500.0 * s_tot[kEmLmax + 1];
-      if (S.iters == 0) {  // initial E-step done: start outer iteration 1
-        S.iters = 1;
-        S.natural = S.forced = 0;
-        S.c = 0;
-        S.act = kActPlan;
-      } else if (S.forced_pending) {  // refresh after a forced annihilation (:931-958)
-        S.act = kActFinishIter;
+    if (pass == kPassDensRefresh) cc++;  // component kept: move on (:819)
+    act = (cc < L) ? kActPlan : kActEndSweep;
+  }
+  while (act != kActDone) {
+    if (act == kActPlan) {
+      // start the update of component cc from the column sums and the moments (:773-801)
+      double tot = 0.0, wkeep = 0.0;
+      for (int l = 0; l < L; l++) {
+        const double wl = max_m(0.0, (S.colsum[l] - nparams / 2.0));
+        if (l == cc) wkeep = wl;
+        tot += wl;
+      }
+      __syncwarp();
+      if (lane == 0) S.lam[cc] = wkeep / tot;
+      comp_steps++;
+      flops += (double)a.n_total * (2.0 * d * d + 8.0 * d + 4.0 * L + 7.0);
+      __syncwarp();
+      v2w_renorm<DMAX>(S, lane);
+      if (S.lam[cc] > 0.005) {
+        // S1, S2 are moments of (x - pivot), pivot = the component's mean before this update:
+        //   mean = pivot + S1/S0,   cov = S2/S0 - (S1/S0)(S1/S0)^T   (:797-810 in shifted form)
+        const double S0 = S.colsum[cc];
+        if (lane < d) {
+          S.dl[lane] = S.S1[lane] / S0;
+          s_mu[cc * d + lane] = s_mu[cc * d + lane] + S.dl[lane];
+        }
+        __syncwarp();
+        for (int q = lane; q < tri; q += 32) {
+          int j = 0;
+          while ((j + 1) * (j + 2) / 2 <= q) j++;
+          const int k = q - j * (j + 1) / 2;
+          S.Bc[q] = (S.S2[q] - S.S1[j] * S.dl[k]) / S0;
+        }
+        __syncwarp();
+        const bool ok = warp_chol<DMAX>(S.Bc, d);
+        __syncwarp();
+        const bool chol_ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+        for (int q = lane; q < tri; q += 32) s_B[cc * tri + q] = S.Bc[q];
+        v2w_make_rec<DMAX>(S, s_mu, s_rec, lane, cc);
+        if (!chol_ok) {
+          status = AMX_ENUMERIC;
+          stop = 1;
+          npass = kPassStop;
+        } else {
+          next = (cc + 1 < L) ? cc + 1 : 0;
+          npass = kPassDensRefresh;
+        }
+        act = kActDone;
+      } else {  // natural annihilation (:821-845): refresh before the next component is looked at
+        v2w_drop<DMAX>(S, s_mu, s_B, lane, cc);
+        L = S.L;
+        v2w_renorm<DMAX>(S, lane);
+        natural = 1;
+        next = (cc < L) ? cc : 0;
+        npass = kPassRefresh;
+        act = kActDone;
+      }
+    } else if (act == kActEndSweep) {
+      cost = v2w_cost<DMAX>(S, lane, a.n_total, nparams, loglik);
+      if (iters == 1) cost_prev = cost;
+      const bool savebest = (iters == 1 || cost < cost_best);  // :881-893
+      if (savebest) {
+        best_L = L;
+        cost_best = cost;
+      }
+      int drop = -1;
+      if (fabs(cost_prev - cost) < min_m(1E-5 * fabs(cost_prev), 0.01) && iters > 1) {  // :894
+        if (L == 1) {
+          stop = 1;
+        } else {
+          forced = 2;
+          double lo = S.lam[0];
+          int gone = 0;
+          for (int l = 1; l < L; l++)
+            if (lo > S.lam[l]) {
+              lo = S.lam[l];
+              gone = l;
+            }
+          drop = gone;
+        }
+      }
+      if (savebest && writer) {
+        if (lane < L) c->best_lam[lane] = S.lam[lane];
+        for (int q = lane; q < L * d; q += 32) c->best_mu[q / d][q % d] = s_mu[q];
+        for (int q = lane; q < L * tri; q += 32) c->best_B[q / tri][q % tri] = s_B[q];
+      }
+      if (drop >= 0) {
+        v2w_drop<DMAX>(S, s_mu, s_B, lane, drop);
+        L = S.L;
+        v2w_renorm<DMAX>(S, lane);
+        forced_pending = 1;
+        next = 0;
+        npass = kPassRefresh;
+        act = kActDone;
       } else {
-        if (pass == kPassDensRefresh) S.c++;  // component kept: move on (:819)
-        S.act = (S.c < S.L) ? kActPlan : kActEndSweep;
+        act = kActFinishIter;
       }
-    }
-    __syncthreads();
-    if (S.forced_pending) {
-      leader_cost<DMAX>(S, a.n_total, nparams);
-      if (t == 0) S.forced_pending = 0;
-      __syncthreads();
-    }
-    while (S.act != kActDone) {
-      const int act = S.act;
-      __syncthreads();
-      if (act == kActPlan) {
-        const int cc = S.c;
-        if (t == 0) {
-          double tot = 0.0, wkeep = 0.0;
-          for (int l = 0; l < S.L; l++) {
-            const double wl = max_m(0.0, (S.colsum[l] - nparams / 2.0));
-            if (l == cc) wkeep = wl;
-            tot += wl;
-          }
-          S.lam[cc] = wkeep / tot;
-          S.comp_steps++;
-          S.flops += (double)a.n_total * (2.0 * d * d + 8.0 * d + 4.0 * S.L + 7.0);
-        }
-        __syncthreads();
-        leader_renorm<DMAX>(S);
-        if (S.lam[cc] > 0.005) {
-          // S1, S2 are moments of (x - pivot), pivot = the component's mean before this update:
-          //   mean = pivot + S1/S0,   cov = S2/S0 - (S1/S0)(S1/S0)^T   (:797-810 in shifted form)
-          const double S0 = S.colsum[cc];
-          if (t < d) {
-            S.dl[t] = S.S1[t] / S0;
-            s_mu[cc * d + t] = s_mu[cc * d + t] + S.dl[t];
-          }
-          __syncthreads();
-          for (int q = t; q < tri; q += nt) {
-            int j = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
-            while ((j + 1) * (j + 2) / 2 <= q) j++;
-            while (j * (j + 1) / 2 > q) j--;
-            const int k = q - j * (j + 1) / 2;
-            S.Bc[q] = (S.S2[q] - S.S1[j] * S.dl[k]) / S0;
-          }
-          __syncthreads();
-          if (t < 32) {
-            const bool ok = warp_chol<DMAX>(S.Bc, d);
-            if (t == 0) S.chol_ok = ok ? 1 : 0;
-          }
-          __syncthreads();
-          for (int q = t; q < tri; q += nt) s_B[cc * tri + q] = S.Bc[q];
-          v2_make_rec<DMAX>(S, s_mu, s_rec, d, cc);
-          if (t == 0) {
-            if (!S.chol_ok) {
-              S.status = AMX_ENUMERIC;
-              S.stop = 1;
-              S.pass = kPassStop;
-            } else {
-              S.next = (cc + 1 < S.L) ? cc + 1 : 0;
-              S.pass = kPassDensRefresh;
-            }
-            S.act = kActDone;
-          }
-        } else {  // natural annihilation (:821-845)
-          v2_drop<DMAX>(S, s_mu, s_B, d, cc);
-          leader_renorm<DMAX>(S);
-          if (t == 0) {
-            S.natural = 1;
-            S.next = (cc < S.L) ? cc : 0;
-            S.pass = kPassRefresh;
-            S.act = kActDone;
-          }
-        }
-      } else if (act == kActEndSweep) {
-        leader_cost<DMAX>(S, a.n_total, nparams);
-        if (t == 0) {
-          if (S.iters == 1) S.cost_prev = S.cost;
-          S.savebest = (S.iters == 1 || S.cost < S.cost_best) ? 1 : 0;  // :881-893
-          if (S.savebest) {
-            S.best_L = S.L;
-            S.cost_best = S.cost;
-          }
-          S.drop = -1;
-          if (fabs(S.cost_prev - S.cost) < min_m(1E-5 * fabs(S.cost_prev), 0.01) && S.iters > 1) {  // :894
-            if (S.L == 1) {
-              S.stop = 1;
-            } else {
-              S.forced = 2;
-              double lo = S.lam[0];
-              int gone = 0;
-              for (int l = 1; l < S.L; l++)
-                if (lo > S.lam[l]) {
-                  lo = S.lam[l];
-                  gone = l;
-                }
-              S.drop = gone;
-            }
-          }
-        }
-        __syncthreads();
-        if (S.savebest && writer) {
-          if (t < S.L) c->best_lam[t] = S.lam[t];
-          for (int q = t; q < S.L * d; q += nt) c->best_mu[q / d][q % d] = s_mu[q];
-          for (int q = t; q < S.L * tri; q += nt) c->best_B[q / tri][q % tri] = s_B[q];
-        }
-        __syncthreads();
-        if (S.drop >= 0) {
-          v2_drop<DMAX>(S, s_mu, s_B, d, S.drop);
-          leader_renorm<DMAX>(S);
-          if (t == 0) {
-            S.forced_pending = 1;
-            S.next = 0;
-            S.pass = kPassRefresh;
-            S.act = kActDone;
-          }
-        } else if (t == 0) {
-          S.act = kActFinishIter;
-        }
-      } else {  // kActFinishIter (:961-970)
-        if (t == 0) {
-          if (S.iters > a.maxit) S.stop = 1;
-          S.cost_prev = S.cost;
-          const int it = S.iters - 1;
-          if (writer) {
-            if (a.trace_ann) a.trace_ann[it] = S.natural + S.forced;
-            if (a.trace_cost) a.trace_cost[it] = S.cost;
-            if (a.trace_loglik) a.trace_loglik[it] = S.loglik;
-            if (a.trace_L) a.trace_L[it] = S.L;
-          }
-          if (S.stop) {
-            S.pass = kPassStop;
-            S.act = kActDone;
-          } else {
-            S.iters++;
-            S.natural = S.forced = 0;
-            S.c = 0;
-            S.act = kActPlan;
-          }
-        }
+    } else {  // kActFinishIter (:961-970)
+      if (iters > a.maxit) stop = 1;
+      cost_prev = cost;
+      const int it = iters - 1;
+      if (writer && lane == 0) {
+        if (a.trace_ann) a.trace_ann[it] = natural + forced;
+        if (a.trace_cost) a.trace_cost[it] = cost;
+        if (a.trace_loglik) a.trace_loglik[it] = loglik;
+        if (a.trace_L) a.trace_L[it] = L;
       }
-      __syncthreads();
+      if (stop) {
+        npass = kPassStop;
+        act = kActDone;
+      } else {
+        iters++;
+        natural = forced = 0;
+        cc = 0;
+        act = kActPlan;
+      }
     }
   }
-  __syncthreads();
+  __syncwarp();
+  if (lane == 0) {
+    S.L = L; S.c = cc; S.next = next; S.iters = iters; S.natural = natural; S.forced = forced; S.stop = stop; S.status = status;
+    S.best_L = best_L; S.pass = npass; S.forced_pending = forced_pending; S.comp_steps = comp_steps; S.flops = flops;
+    S.loglik = loglik; S.cost = cost; S.cost_prev = cost_prev; S.cost_best = cost_best;
+  }
+  __syncwarp();
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
   unsigned epoch = 0;
   unsigned long long seq_base = 0;  // stages used by the passes so far (ring position and mbarrier parity)
   int pass = kPassInitStats;
-  long long dbg_pass = 0, dbg_bar = 0, dbg_lead = 0;
+  long long dbg_pass = 0, dbg_bar = 0, dbg_lead = 0, dbg_x1 = 0, dbg_x2 = 0;
 
   for (;;) {
     const long long tk0 = clock64();
@@ -573,8 +574,10 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
           tma_load_row(Es + l0 * kV2TS, a.E + ((size_t)tl * Lmax + S.slot[l0]) * kV2TS, (uint32_t)(len * kV2TS * 8), &s_full[st]);
         }
       };
-      // prologue: the ring is idle (end-of-pass barrier): warp 0 fills it
+      // prologue: the ring is idle (end-of-pass barrier): warp 0 fills it.  The density rows it copies were written
+      // with ordinary stores during the previous pass: order those before the bulk copies (async proxy) too.
       fence_proxy_async();
+      asm volatile("fence.proxy.async.global;" ::: "memory");
       if (warp == 0)
         for (int it = 0; it < NS && it < ntile_cta; it++) fetch(it);
       {
@@ -584,6 +587,13 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
         double ll = 0.0, nfb = 0.0;
         const int cslot = dens ? S.slot[cc] : 0;
         const double *lam = S.lam;
+        // T_l = sum_i E_il inv_i gives the column sums as lam_l T_l only while every weight is a positive number.  Once a
+        // weight is NaN (the unguarded first E-step can poison them, :737-745) the reference's guarded refresh falls
+        // back to uniform responsibilities and RECOVERS; lam_l T_l could not.  Such a pass accumulates the
+        // responsibilities themselves (`direct`: the column holds w_il, the leader takes the sums as they are).
+        bool direct = false;
+        for (int l = 0; l < L; l++) direct |= !(lam[l] > 0.0);
+        if (t == 0) S.keep = direct ? 1 : 0;
         for (int it = team; it < ntile_cta; it += NTEAM) {
           const unsigned long long seq = seq_base + (unsigned long long)it;
           const int st = (int)(seq % (unsigned)NS);
@@ -658,12 +668,16 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
               Ecol[l * kV2TS] = w / lam[l];
               if (l == nx) wn = w;
             }
-          } else if (sum >= 1e-280) {  // the reference's guard (:855-866) holds, and 1/sum is safe
+          } else if (sum >= 1e-280 && !direct) {  // the reference's guard (:855-866) holds, and 1/sum is safe
             inv = 1.0 / sum;
             ll += log(sum);
             wn = (lam[nx] * Ecol[nx * kV2TS]) * inv;
+          } else if (sum >= 1e-280) {  // (unreachable while a weight is NaN -- the sum is NaN then -- kept for weights <= 0)
+            const double is = 1.0 / sum;
+            ll += log(sum);
+            for (int l = 0; l < L; l++) Ecol[l * kV2TS] = (lam[l] * Ecol[l * kV2TS]) * is;
           } else {
-            wn = v2_slow_sample(lam, s_mu, s_B, d, tri, L, nx, sum, xs + tt, Ecol, &ll, &nfb);
+            wn = v2_slow_sample(lam, s_mu, s_B, d, tri, L, nx, sum, direct, xs + tt, Ecol, &ll, &nfb);
           }
           winv[tt] = inv;
           (void)wn;  // the B-phase forms w_next = lam_nx E_i,nx inv itself (in the rewritten cases that is w to an ulp)
@@ -679,7 +693,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
           named_bar(1 + team, 128);
           // ---- B-phase: warp wq owns the entries e = wq (mod 4) of (S2 | S1) over all 128 samples
           {
-            const double lam_nx = (nx < L) ? lam[nx] : 0.0;  // empty mixture: no weight
+            const double lam_nx = (nx < L) ? (direct ? 1.0 : lam[nx]) : 0.0;  // empty mixture: no weight
             v2_bphase_any<DMAX>(acc, wq, xs, Es, Es + nx * kV2TS, lam_nx, winv, lane, d, L);
           }
           // the stage is free once all four warps are through; the team refills it with the tile NS places ahead
@@ -752,6 +766,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     }
     __syncthreads();
     const int par = (int)(epoch & 1u);
+    const long long tx1 = clock64();
     if (s_flag) {
       // last CTA of this GPU: sum the GPU's partial rows (lanes over consecutive CTAs of one value: coalesced;
       // fixed order), then post the row to every GPU's inbox and raise this GPU's flag there
@@ -803,6 +818,9 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       }
     }
     __syncthreads();
+    const long long tx2 = clock64();
+    dbg_x1 += tx1 - tk1;
+    dbg_x2 += tx2 - tx1;
     if (S.stop == 2) {
       if (writer && t == 0) atomicExch(&ctrl->status, AMX_ECUDA);
       return;
@@ -815,7 +833,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     epoch++;
     __syncthreads();
     const long long tk2 = clock64();
-    v2_leader<DMAX>(a, ctrl, writer, pass, s_tot, S, s_mu, s_B, s_rec);
+    if (warp == 0) v2_leader_warp<DMAX>(a, ctrl, writer, pass, s_tot, S, s_mu, s_B, s_rec);
+    __syncthreads();
     const long long tk3 = clock64();
     dbg_pass += tk1 - tk0;
     if (v.debug && t == 0) me->dbg_cta[blockIdx.x < 160 ? blockIdx.x : 159] = dbg_pass;
@@ -831,7 +850,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       ctrl->pass = S.pass; ctrl->L = S.L; ctrl->c = S.c; ctrl->next = S.next; ctrl->iters = S.iters; ctrl->stop = S.stop;
       ctrl->status = S.status; ctrl->best_L = S.best_L; ctrl->comp_steps = S.comp_steps; ctrl->flops = S.flops;
       ctrl->loglik = S.loglik; ctrl->cost = S.cost; ctrl->cost_prev = S.cost_prev; ctrl->cost_best = S.cost_best;
-      ctrl->dbg[0] = dbg_pass; ctrl->dbg[1] = dbg_bar; ctrl->dbg[3] = dbg_lead;
+      ctrl->dbg[0] = dbg_pass; ctrl->dbg[1] = dbg_bar; ctrl->dbg[3] = dbg_lead; ctrl->dbg[4] = dbg_x1; ctrl->dbg[5] = dbg_x2;
     }
     const int Lw = S.L < 0 ? 0 : S.L;
     if (t < kEmLmax) {
