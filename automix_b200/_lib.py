@@ -41,7 +41,7 @@ _lib = None
 EXPORTS = [
     "amx_last_error", "amx_version", "amx_device_count", "amx_set_device", "amx_set_stream",
     "amx_synchronize", "amx_set_deferred_sync", "amx_release_workspace", "amx_launch_count", "amx_measure_fp64_peak", "amx_mix_logpdf",
-    "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine",
+    "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine", "amx_target_mixnorm",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
     "amx_rj_set_tape", "amx_rj_set_pk_mode", "amx_rj_get_pk_shared", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
@@ -80,6 +80,8 @@ def lib():
     L.amx_target_quad.restype = C.c_void_p
     L.amx_target_quad.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp]
     L.amx_target_coalmine.restype = C.c_void_p
+    L.amx_target_mixnorm.restype = C.c_void_p
+    L.amx_target_mixnorm.argtypes = [C.c_int, _ip, C.c_int, _dp, _dp]
     L.amx_target_host_scalar.restype = C.c_void_p
     L.amx_target_host_scalar.argtypes = [C.c_int, _ip, C.c_void_p]
     L.amx_target_host_batched.restype = C.c_void_p
@@ -212,6 +214,9 @@ class Target:
                                        _d(f64(hi)) if hi is not None else None)
         elif kind == "coalmine":
             self.h = L.amx_target_coalmine()
+        elif kind == "mixnorm":
+            self.h = L.amx_target_mixnorm(len(self.dims), _i(i32(spec["ncomp"])), len(spec["y"]), _d(f64(spec["y"])),
+                                          _d(f64(spec["prior"])))
         else:
             raise ValueError(kind)
         if not self.h:

@@ -205,6 +205,47 @@ amx_target *amx_target_coalmine(void) {
   return t;
 }
 
+amx_target *amx_target_mixnorm(int nmodels, const int *ncomp, int ndata, const double *y, const double *prior5) {
+  if (require_device()) return nullptr;
+  if (nmodels < 1 || nmodels > AMX_MAX_MODELS || !ncomp || ndata < 1 || !y || !prior5) {
+    fail(AMX_EINVAL, "amx_target_mixnorm: bad arguments");
+    return nullptr;
+  }
+  int dims[AMX_MAX_MODELS];
+  for (int k = 0; k < nmodels; k++) {
+    if (ncomp[k] < 1 || ncomp[k] > kMixNormKmax) {
+      fail(AMX_EINVAL, "amx_target_mixnorm: 1..%d components per model (model %d has %d)", kMixNormKmax, k, ncomp[k]);
+      return nullptr;
+    }
+    dims[k] = 3 * ncomp[k] - 1;
+  }
+  if (!(prior5[0] > 0.0 && prior5[2] > 0.0 && prior5[4] > 0.0)) {
+    fail(AMX_EINVAL, "amx_target_mixnorm: prior standard deviations must be positive");
+    return nullptr;
+  }
+  amx_target *t = new_target(kTargetMixNorm, nmodels, dims);
+  if (!t) return nullptr;
+  amx_fam_hdr h;
+  memset(&h, 0, sizeof(h));
+  h.nmodels = nmodels;
+  for (int k = 0; k < nmodels; k++) {
+    h.dims[k] = dims[k];
+    h.ncomp[k] = ncomp[k];
+    if (dims[k] > h.dmax) h.dmax = dims[k];
+    if (ncomp[k] > h.Lmax) h.Lmax = ncomp[k];
+  }
+  std::vector<double> data;
+  data.push_back((double)ndata);
+  for (int i = 0; i < 5; i++) data.push_back(prior5[i]);
+  for (int i = 0; i < ndata; i++) data.push_back(y[i]);
+  h.total = (int)data.size();
+  if (upload_blob(h, data.data(), &t->d.blob_dev, &t->d.blob_bytes)) {
+    free(t);
+    return nullptr;
+  }
+  return t;
+}
+
 amx_target *amx_target_host_scalar(int nmodels, const int *dims, amx_scalar_fn f) {
   amx_target *t = new_target(kTargetHostScalar, nmodels, dims);
   if (t) t->d.scalar = f;

@@ -1871,7 +1871,9 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   cudaSetDevice(home);
   if (rc != AMX_OK) return rc;
   if (status == AMX_ECUDA) return fail(status, "EM fit: a GPU stopped answering at the cross-GPU barrier");
-  if (status) return fail(status, "EM fit: scatter matrix not positive definite");
+  if (status && !use_v2) return fail(status, "EM fit: scatter matrix not positive definite");
+  // (second generation: a non-positive-definite scatter is carried as the reference carries it -- see v2_leader_warp --
+  // and reported in res->status only)
   return AMX_OK;
 }
 

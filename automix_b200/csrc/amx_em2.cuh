@@ -270,7 +270,7 @@ __device__ __forceinline__ void v2w_make_rec(LeaderS<DMAX> &S, const double *s_m
 
 template <int DMAX>
 __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass, const double *s_tot, LeaderS<DMAX> &S,
-                               double *s_mu, double *s_B, double *s_rec) {
+                               double *s_mu, double *s_B, double *s_rec, double *s_piv) {
   constexpr int d = DMAX, tri = d * (d + 1) / 2, nparams = d + tri;
   const int lane = threadIdx.x & 31;
   if (pass == kPassInitStats) {
@@ -299,6 +299,8 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
     }
     __syncwarp();
     v2w_make_rec<DMAX>(S, s_mu, s_rec, lane, 0);
+    if (lane < d) s_piv[lane] = s_mu[lane];  // pivot of the first pass: the mean of component 0
+    __syncwarp();
     return;
   }
   // a refresh finished: s_tot = [T_l (Lmax) | loglik | fallbacks | S1 (d) | S2 (tri)], column sums are lam_l T_l
@@ -335,20 +337,18 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
         if (l == cc) wkeep = wl;
         tot += wl;
       }
-      __syncwarp();
-      if (lane == 0) S.lam[cc] = wkeep / tot;
-      comp_steps++;
-      flops += (double)a.n_total * (2.0 * d * d + 8.0 * d + 4.0 * L + 7.0);
-      __syncwarp();
-      v2w_renorm<DMAX>(S, lane);
-      if (S.lam[cc] > 0.005) {
-        // S1, S2 are moments of (x - pivot), pivot = the component's mean before this update:
+      // the weight this component is about to get (:785-792), formed without touching the weights yet: a re-pivot
+      // pass (below) must see the weights the moments were formed with
+      const double lam_cc = wkeep / tot;
+      double lsum = 0.0;
+      for (int l = 0; l < L; l++) lsum += (l == cc) ? lam_cc : S.lam[l];
+      const bool kept = (lam_cc / lsum) > 0.005;
+      const double S0 = S.colsum[cc];
+      if (kept) {
+        // S1, S2 are moments of (x - pivot), pivot = s_piv (the component's mean before this update):
         //   mean = pivot + S1/S0,   cov = S2/S0 - (S1/S0)(S1/S0)^T   (:797-810 in shifted form)
-        const double S0 = S.colsum[cc];
-        if (lane < d) {
-          S.dl[lane] = S.S1[lane] / S0;
-          s_mu[cc * d + lane] = s_mu[cc * d + lane] + S.dl[lane];
-        }
+        __syncwarp();
+        if (lane < d) S.dl[lane] = S.S1[lane] / S0;
         __syncwarp();
         for (int q = lane; q < tri; q += 32) {
           int j = 0;
@@ -357,19 +357,47 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
           S.Bc[q] = (S.S2[q] - S.S1[j] * S.dl[k]) / S0;
         }
         __syncwarp();
+        // The shifted form cancels (S1/S0)^2 out of S2/S0: harmless while the mean moves by less than a few standard
+        // deviations per step (always, in a fit that is converging), but a component collapsing onto a few (duplicate)
+        // samples can have a variance many orders below its squared shift.  Then the moments are taken again about
+        // the NEW mean (one extra pass, same weights), which is the reference's centred formula (:803-810) to rounding.
+        bool cancels = false;
+        for (int j = 0; j < d; j++) cancels |= !(S.Bc[AMX_TRI(j, j)] * 1000.0 > S.dl[j] * S.dl[j]);
+        if (cancels && !S.drop) {
+          if (lane < d) s_piv[lane] = s_piv[lane] + S.dl[lane];
+          if (lane == 0) S.drop = 1;  // re-pivot pass in flight
+          __syncwarp();
+          next = cc;
+          npass = kPassRefresh;
+          act = kActDone;
+          continue;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        S.lam[cc] = lam_cc;
+        S.drop = 0;
+      }
+      comp_steps++;
+      flops += (double)a.n_total * (2.0 * d * d + 8.0 * d + 4.0 * L + 7.0);
+      __syncwarp();
+      v2w_renorm<DMAX>(S, lane);
+      if (kept) {
+        if (lane < d) s_mu[cc * d + lane] = s_piv[lane] + S.dl[lane];
+        __syncwarp();
         const bool ok = warp_chol<DMAX>(S.Bc, d);
         __syncwarp();
         const bool chol_ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
         for (int q = lane; q < tri; q += 32) s_B[cc * tri + q] = S.Bc[q];
         v2w_make_rec<DMAX>(S, s_mu, s_rec, lane, cc);
-        if (!chol_ok) {
-          status = AMX_ENUMERIC;
-          stop = 1;
-          npass = kPassStop;
-        } else {
-          next = (cc + 1 < L) ? cc + 1 : 0;
-          npass = kPassDensRefresh;
-        }
+        // A scatter matrix that is not positive definite even about its own mean (a component sitting on identical
+        // samples): the reference takes sqrt of a non-positive pivot (:1691) and carries on with NaN / zero entries --
+        // samples whose density turns NaN get uniform responsibilities and the -500 penalty (:855-866), the iteration
+        // cap ends a fit that never recovers, and the minimum-cost mixture seen is returned.  Same here; the status
+        // word records that it happened.
+        if (!chol_ok) status = AMX_ENUMERIC;
+        next = (cc + 1 < L) ? cc + 1 : 0;
+        npass = kPassDensRefresh;
         act = kActDone;
       } else {  // natural annihilation (:821-845): refresh before the next component is looked at
         v2w_drop<DMAX>(S, s_mu, s_B, lane, cc);
@@ -442,6 +470,8 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
     }
   }
   __syncwarp();
+  // pivot of the next pass: the current mean of the component whose moments it forms (unless a re-pivot set it)
+  if (!S.drop && lane < d && next < kEmLmax) s_piv[lane] = s_mu[next * d + lane];
   if (lane == 0) {
     S.L = L; S.c = cc; S.next = next; S.iters = iters; S.natural = natural; S.forced = forced; S.stop = stop; S.status = status;
     S.best_L = best_L; S.pass = npass; S.forced_pending = forced_pending; S.comp_steps = comp_steps; S.flops = flops;
@@ -480,7 +510,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
   double *s_mu = smem + v.region0_doubles;           // [Lmax][d]
   double *s_B = s_mu + Lmax * d;                     // [Lmax][tri]
   double *s_rec = s_B + Lmax * tri;                  // family record of the component in progress
-  double *s_tot = s_rec + (AMX_REC_HEAD + 2 * DMAX + TRI);  // [kV2NV] totals over all CTAs and GPUs
+  double *s_piv = s_rec + (AMX_REC_HEAD + 2 * DMAX + TRI);  // [DMAX] pivot of the moments of this pass
+  double *s_tot = s_piv + DMAX + (DMAX & 1);          // [kV2NV] totals over all CTAs and GPUs
   double *s_part = s_tot + kV2NV;                    // [kV2NV] this CTA's partial row
   LeaderS<DMAX> &S = *reinterpret_cast<LeaderS<DMAX> *>(s_part + kV2NV);
   const int NS = v.ns;
@@ -683,7 +714,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
           (void)wn;  // the B-phase forms w_next = lam_nx E_i,nx inv itself (in the rewritten cases that is w to an ulp)
           // shift by the pivot (current mean of the next component): the rows become dx = x - pivot
           {
-            const double *piv = s_mu + nx * d;
+            const double *piv = s_piv;
 #pragma unroll
             for (int j = 0; j < DMAX; j++) {
               const double v0 = xv[j] - piv[j];
@@ -833,7 +864,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     epoch++;
     __syncthreads();
     const long long tk2 = clock64();
-    if (warp == 0) v2_leader_warp<DMAX>(a, ctrl, writer, pass, s_tot, S, s_mu, s_B, s_rec);
+    if (warp == 0) v2_leader_warp<DMAX>(a, ctrl, writer, pass, s_tot, S, s_mu, s_B, s_rec, s_piv);
     __syncthreads();
     const long long tk3 = clock64();
     dbg_pass += tk1 - tk0;
@@ -876,7 +907,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
 
 template <int DMAX>
 constexpr size_t v2_fixed_doubles(int d, int Lmax) {
-  return (size_t)Lmax * d + (size_t)Lmax * (d * (d + 1) / 2) + (AMX_REC_HEAD + 2 * DMAX + V2Cfg<DMAX>::TRI) + 2 * kV2NV +
+  return (size_t)Lmax * d + (size_t)Lmax * (d * (d + 1) / 2) + (AMX_REC_HEAD + 2 * DMAX + V2Cfg<DMAX>::TRI) + DMAX + 1 + 2 * kV2NV +
          (sizeof(LeaderS<DMAX>) + 7) / 8 + 2;
 }
 template <int DMAX, int NTEAM>

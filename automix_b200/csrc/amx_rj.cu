@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "amx_internal.cuh"
+#include "amx_mailbox.cuh"
 #include "amx_rj.cuh"
 
 namespace amx {
@@ -426,6 +427,98 @@ __global__ void __launch_bounds__(kRjThreads) rj_split_kernel(RjLaunch a, RjSpli
   if (status && active) atomicOr(a.status, status);
 }
 
+
+// ---- persistent sweep kernel for HOST log-posterior callbacks (amx_mailbox.cuh) -------------------------------------
+// The whole sweep loop of the fused kernel with the plug-in evaluation replaced by a mailbox exchange with the host:
+// chain state stays in the thread for all nsweeps sweeps.  Every CTA makes the same number of exchanges: a block-move
+// sweep has one, any other sweep dmax (chains of smaller models sit the extra coordinates out), then one for the jump.
+template <class RNG>
+__global__ void __launch_bounds__(kMbThreads) rj_mailbox_kernel(RjLaunch a, void *mb_base, int ldx, unsigned seq0, int cpc) {
+  using CFG = RjCfgG;
+  __shared__ unsigned s_hist[kMbThreads / 32][CFG::NMAX];  // (the CTA may be launched with fewer than kMbThreads threads)
+  __shared__ int s_clp[AMX_MAX_MODELS];
+  __shared__ unsigned long long s_cnt[8];
+  AllocVec<CFG> pa;
+  ProposalView P;
+  P.bind(a.prop_blob);
+  const int nm = P.h->nmodels, dmax = a.st.dmax;
+  for (int i = threadIdx.x; i < (kMbThreads / 32) * CFG::NMAX; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+  if (threadIdx.x < AMX_MAX_MODELS) s_clp[threadIdx.x] = 0;
+  if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  Mailbox *mb = mailbox_at(mb_base, blockIdx.x, ldx);
+  unsigned seq = seq0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // cpc chains per CTA (the first cpc threads): few chains per mailbox keep the host's share of an exchange short, and
+  // the CTAs' exchanges overlap
+  const long gid = (long)blockIdx.x * cpc + threadIdx.x;
+  const bool active = (int)threadIdx.x < cpc && gid < a.st.C;
+  const long id = active ? gid : a.st.C - 1;  // the other threads shadow the last chain: they ask for nothing and never write
+  ChainRegs<CFG> c;
+  load_chain(c, a.st, id, a.pk_shared);
+  RNG u;
+  const unsigned long long draws0 = a.st.draws[id];
+  open_stream(u, a, id, draws0);
+  const bool traced = active && gid < a.ntrace;
+  int status = 0;
+  for (int s = 0; s < a.nsweeps; s++) {
+    const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
+    const int d = P.h->dims[c.k];
+    if (sweep_i % 10ull == 0ull) {
+      rwm_block_propose(c, P, u, a.modes);
+      const double lpn = mailbox_exchange<CFG::DMAX>(mb, ldx, ++seq, active ? c.k : -1, c.thn, d);
+      rwm_block_finish(c, P, u, lpn);
+    } else {
+      sync_proposal(c, d);
+      for (int j = 0; j < dmax; j++) {
+        const bool on = j < d;
+        if (on) rwm_coord_propose(c, P, u, j, a.modes);
+        const double lpn = mailbox_exchange<CFG::DMAX>(mb, ldx, ++seq, (active && on) ? c.k : -1, c.thn, d);
+        if (on) rwm_coord_finish(c, u, j, lpn);
+      }
+    }
+    rj_propose(c, P, u, a.gam[s], a.modes, s_clp, pa);
+    {
+      const double lpn = mailbox_exchange<CFG::DMAX>(mb, ldx, ++seq, active ? c.kn : -1, c.thn, P.h->dims[c.kn]);
+      rj_finish(c, P, u, lpn, a.adapt != 0);
+    }
+    if (active && c.lp != c.lp) status |= 2;
+    __syncwarp();
+    for (int m = 0; m < nm; m++) {
+      const unsigned b = __ballot_sync(0xffffffffu, active && c.k == m);
+      if (lane == 0) s_hist[warp][m] += __popc(b);
+    }
+    if (traced) {
+      const long row = (long)gid * a.tr_stride + a.tr_off + s;
+      a.tr_k[row] = c.k;
+      a.tr_lp[row] = c.lp;
+      const int dk = P.h->dims[c.k];
+      for (int i = 0; i < dmax; i++) a.tr_theta[row * dmax + i] = (i < dk) ? c.th[i] : 0.0;
+      for (int q = 0; q < nm; q++) a.tr_pk[row * nm + q] = c.pk[q];
+    }
+  }
+  if (active && u.overrun()) status |= 1;
+  if (active) {
+    store_chain(c, a.st, id);
+    a.st.draws[id] = u.n;
+  }
+  unsigned long long v[8] = {c.acc_b, c.try_b, c.acc_s, c.try_s, c.acc_j, c.try_j, 0ull, u.n - draws0};
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const unsigned long long r = warp_sum_u64(active ? v[q] : 0ull);
+    if (lane == 0) atomicAdd(&s_cnt[q], r);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && s_cnt[threadIdx.x]) atomicAdd(&a.cnt[threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < nm) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_hist[w][threadIdx.x];
+    atomicAdd(&a.visits[threadIdx.x], t);
+    atomicAdd(&a.visits_grp[(blockIdx.x % kRjGroups) * AMX_MAX_MODELS + threadIdx.x], t);
+  }
+  if (status && active) atomicOr(a.status, status);
+}
+
 // chain start for host callbacks: pick the model and copy the start vector; lp comes from the host
 template <class RNG>
 __global__ void __launch_bounds__(kRjThreads) rj_init_split_kernel(RjLaunch a, RjSplit sp, const double *init_flat,
@@ -554,6 +647,8 @@ struct amx_rj {
   double *stage_dev;  // chain-major staging for set/get_state
   long stage_cap;
   // host-callback mode
+  void *mb_host;  // mailboxes (mapped pinned host memory), one per CTA of rj_mailbox_kernel
+  unsigned mb_seq;  // exchanges they have carried so far
   RjSplit sp;
   double *h_thn, *h_lpn;  // pinned mirrors
   int *h_keval;
@@ -596,7 +691,7 @@ static int launch_sweeps(const RjLaunch &a) {
 
 template <class TGT, class RNG>
 static int launch_cfg(const RjLaunch &a, int dmax, int Lmax, int nm) {
-  if constexpr (std::is_same<TGT, CoalTarget>::value) {
+  if constexpr (TargetIsWide<TGT>::value) {
     if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
     return launch_sweeps<RjCfgG, TGT, RNG>(a);
   } else {
@@ -615,6 +710,7 @@ static int launch_tgt(const amx_rj *rj, const RjLaunch &a) {
     case kTargetGaussMix: return launch_cfg<GaussMixTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
     case kTargetQuad: return launch_cfg<QuadTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
     case kTargetCoal: return launch_cfg<CoalTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
+    case kTargetMixNorm: return launch_cfg<MixNormTarget, RNG>(a, h.dmax, h.Lmax, h.nmodels);
   }
   return fail(AMX_EINVAL, "plug-in kind %d has no fused sweep kernel", rj->tgt->d.kind);
 }
@@ -704,6 +800,40 @@ static int split_phase(amx_rj *rj, const RjLaunch &a, int phase, int j, int s) {
   count_launch();
   AMX_CUDA(cudaGetLastError());
   return AMX_OK;
+}
+
+// host callbacks through the mailbox: launch the persistent kernel, then serve it from this thread until every CTA
+// has had all its values (AMX_HOST_MAILBOX=0 keeps the kernel-per-evaluation path below)
+static int mailbox_sweeps(amx_rj *rj, RjLaunch &a) {
+  const char *ce = getenv("AMX_MAILBOX_CPC");
+  int cpc = ce ? atoi(ce) : 32;
+  cpc = cpc < 1 ? 1 : (cpc > kMbThreads ? kMbThreads : cpc);
+  const int ncta = (int)((rj->C + cpc - 1) / cpc), ldx = rj->dmax;
+  if (!rj->mb_host)
+    if (int rc = mailbox_alloc(&rj->mb_host, ncta, ldx)) return rc;
+  long nexch = 0;
+  for (int s = 0; s < a.nsweeps; s++) nexch += (((a.sweep0 + (unsigned long long)s) % 10ull == 0ull) ? 1 : rj->dmax) + 1;
+  if (rj->mb_seq + (unsigned long long)nexch > 0xFFFFFF00ull) {  // 32-bit request numbers: start a fresh set of mailboxes
+    AMX_CUDA(cudaStreamSynchronize(stream()));
+    cudaFreeHost(rj->mb_host);
+    rj->mb_host = nullptr;
+    rj->mb_seq = 0;
+    if (int rc = mailbox_alloc(&rj->mb_host, ncta, ldx)) return rc;
+  }
+  const int nthr = (cpc + 31) / 32 * 32;  // no more threads than chains: every thread of the CTA writes its slot each exchange
+  if (rj->tape_dev) rj_mailbox_kernel<TapeStream><<<ncta, nthr, 0, stream()>>>(a, rj->mb_host, ldx, rj->mb_seq, cpc);
+  else rj_mailbox_kernel<PhiloxStream><<<ncta, nthr, 0, stream()>>>(a, rj->mb_host, ldx, rj->mb_seq, cpc);
+  count_launch();
+  AMX_CUDA(cudaGetLastError());
+  std::vector<MbJob> jobs(1);
+  jobs[0] = {rj->mb_host, ncta, ldx, nthr, nexch, stream(), rj->mb_seq};
+  rj->mb_seq += (unsigned)nexch;
+  if (int rc = mailbox_serve(jobs, rj->tgt->d)) return rc;
+  return AMX_OK;
+}
+static bool use_mailbox() {
+  const char *e = getenv("AMX_HOST_MAILBOX");
+  return !(e && atoi(e) == 0);
 }
 
 static int split_sweeps(amx_rj *rj, RjLaunch &a) {
@@ -809,6 +939,7 @@ void amx_rj_destroy(amx_rj *rj) {
   moments_free(rj->mom);
   cudaFree(rj->stage_dev);
   cudaFree(rj->sp.thn); cudaFree(rj->sp.keval); cudaFree(rj->sp.lpn); cudaFree(rj->sp.kn); cudaFree(rj->sp.carry);
+  if (rj->mb_host) cudaFreeHost(rj->mb_host);
   if (rj->h_thn) cudaFreeHost(rj->h_thn);
   if (rj->h_lpn) cudaFreeHost(rj->h_lpn);
   if (rj->h_keval) cudaFreeHost(rj->h_keval);
@@ -926,6 +1057,10 @@ int amx_rj_init_chains(amx_rj *rj) {
       if (tape) rj_init_kernel<CoalTarget, TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
       else rj_init_kernel<CoalTarget, PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
       break;
+    case kTargetMixNorm:
+      if (tape) rj_init_kernel<MixNormTarget, TapeStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      else rj_init_kernel<MixNormTarget, PhiloxStream><<<grid, kRjThreads, 0, stream()>>>(a, rj->init_dev);
+      break;
     default:
       return fail(AMX_EINVAL, "plug-in kind %d has no device chain start", rj->tgt->d.kind);
   }
@@ -1042,7 +1177,7 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
     a.sweep0 = rj->sweep_i + (unsigned long long)off;
     a.nsweeps = (int)m;
     a.tr_off = off;
-    if (is_host_target(rj)) rc = split_sweeps(rj, a);
+    if (is_host_target(rj)) rc = use_mailbox() ? mailbox_sweeps(rj, a) : split_sweeps(rj, a);
     else rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
     if (rc == AMX_OK && pop) {  // also while burning: the histogram baseline must follow the visits
       rj_pk_population_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->visits_dev, a.gam, (int)m, rj->nm, adapt);
@@ -1167,6 +1302,9 @@ int amx_target_eval(const amx_target *t, long n, const int *model_k, const doubl
       break;
     case kTargetCoal:
       target_eval_kernel<CoalTarget><<<grid, kRjThreads, 0, stream()>>>(t->d.blob_dev, t->d.flags, n, k_dev, x_dev, ldx, o_dev);
+      break;
+    case kTargetMixNorm:
+      target_eval_kernel<MixNormTarget><<<grid, kRjThreads, 0, stream()>>>(t->d.blob_dev, t->d.flags, n, k_dev, x_dev, ldx, o_dev);
       break;
   }
   count_launch();

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "amx_internal.cuh"
+#include "amx_mailbox.cuh"
 #include "amx_targets.cuh"
 
 namespace amx {
@@ -537,6 +538,95 @@ __global__ void __launch_bounds__(kRwmThreads) rwm_split_kernel(RwmArgs a, RwmSp
   if (status) atomicOr(a.status, status);
 }
 
+// ---- persistent form for HOST callbacks (amx_mailbox.cuh) -------------------------------------------------------------
+// The chain of rwm_split_kernel kept in one thread for its whole schedule; every log-posterior value comes from the
+// host through the CTA's mailbox.  Every sweep makes exactly d exchanges (a block-move sweep uses the first and sits
+// the others out), plus one for the start point, so that the host knows each CTA's count.
+template <class RNG>
+__global__ void __launch_bounds__(kMbThreads) rwm_mailbox_kernel(RwmArgs a, void *mb_base, int ldx) {
+  constexpr int DM = AMX_MAX_DIM;
+  const long gid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = gid < a.nchains;
+  const long id = active ? gid : a.nchains - 1;
+  const int d = a.d, k = active ? a.model_k : -1;
+  Mailbox *mb = mailbox_at(mb_base, blockIdx.x, ldx);
+  unsigned seq = 0;
+  RNG u;
+  if constexpr (std::is_same<RNG, TapeStream>::value) u.open(a.tape, a.tape_stride, (unsigned long long)id, 0ull);
+  else u.open(a.seed, (unsigned long long)id, 0ull);
+  double cur[DM], prop[DM], sig[DM];
+  int nacc[DM], ntry[DM];
+  for (int i = 0; i < DM; i++) {
+    cur[i] = prop[i] = (i < d) ? a.init[i] : 0.0;
+    sig[i] = 10.0;  // :595
+    nacc[i] = ntry[i] = 0;
+  }
+  const double alphastar = 0.25;
+  double lp = mailbox_exchange<DM>(mb, ldx, ++seq, k, prop, d);  // :599
+  long stored = 0;
+  for (int sweep = 1; sweep <= a.nsweepr; sweep++) {
+    const double uu = u.next();
+    if (sweep > a.nburn && uu < 0.1) {  // block move, no adaptation (:606-617)
+      int i = 0;
+      for (; i + 1 < d; i += 2) {
+        double z0, z1;
+        gauss_pair(u, z0, z1);
+        prop[i] = z0;
+        prop[i + 1] = z1;
+      }
+      if (d & 1) prop[d - 1] = gauss_single(u);
+      const double den = a.dof > 0 ? t_divisor(a.dof, u) : 1.0;
+      for (int q = 0; q < d; q++) prop[q] = fma(sig[q], a.dof > 0 ? prop[q] / den : prop[q], cur[q]);
+      const double lpn = mailbox_exchange<DM>(mb, ldx, ++seq, k, prop, d);
+      if (u.next() < mh_prob(lpn - lp)) {
+        for (int q = 0; q < d; q++) cur[q] = prop[q];
+        lp = lpn;
+      } else {
+        for (int q = 0; q < d; q++) prop[q] = cur[q];
+      }
+      for (int j = 1; j < d; j++) mailbox_exchange<DM>(mb, ldx, ++seq, -1, prop, d);
+    } else {  // one coordinate after the other, scales adapted towards 25 % acceptance (:619-640)
+      const double gam = a.gtab[sweep - 1];
+      for (int i = 0; i < d; i++) {
+        double z = gauss_single(u);
+        if (a.dof > 0) z /= t_divisor(a.dof, u);
+        prop[i] = fma(sig[i], z, cur[i]);
+        const double lpn = mailbox_exchange<DM>(mb, ldx, ++seq, k, prop, d);
+        const double acc = min_m(1.0, mh_prob(lpn - lp));
+        if (u.next() < acc) {
+          nacc[i]++;
+          ntry[i]++;
+          cur[i] = prop[i];
+          lp = lpn;
+          sig[i] = max_m(0.0, sig[i] - gam * (alphastar - 1.0));
+        } else {
+          ntry[i]++;
+          prop[i] = cur[i];
+          sig[i] = max_m(0.0, sig[i] - gam * alphastar);
+        }
+      }
+    }
+    const int remain = a.nsweepr - sweep;  // :642-655
+    if (active && remain < 10000 * d && remain % 10 == 0) {
+      if (stored < 1000L * d)
+        for (int i = 0; i < d; i++) a.samples_out[((size_t)id * 1000 * d + stored) * d + i] = cur[i];
+      stored++;
+    }
+    if (sweep % 100 == 0 && gid == 0 && a.sig_trace0 != nullptr) {
+      const int row = sweep / 100 - 1;
+      for (int i = 0; i < d; i++) {
+        a.sig_trace0[(size_t)row * d + i] = sig[i];
+        a.acc_trace0[(size_t)row * d + i] = (double)nacc[i] / (double)ntry[i];
+      }
+    }
+  }
+  if (active) {
+    for (int i = 0; i < d; i++) a.sig_out[(size_t)id * d + i] = sig[i];
+    const int status = (u.overrun() ? 1 : 0) | ((lp != lp) ? 2 : 0);
+    if (status) atomicOr(a.status, status);
+  }
+}
+
 // Few chains: latency is what matters, give each chain a warp (speculative kernel).  Many chains (pooled
 // stage-1 populations): throughput matters, one thread per chain.  Student-t proposals draw a data-dependent
 // number of uniforms per step (rgamma's rejection loop), which the look-ahead cannot index: sequential kernel.
@@ -550,7 +640,7 @@ template <class TGT, class RNG>
 static int rwm_launch_d(const RwmArgs &a) {
   if (rwm_use_spec(a)) {
     const unsigned g = (unsigned)a.nchains;
-    if constexpr (std::is_same<TGT, CoalTarget>::value) {
+    if constexpr (TargetIsWide<TGT>::value) {
       rwm_spec_kernel<AMX_MAX_DIM, TGT, RNG><<<g, 32, 0, stream()>>>(a);
     } else {
       if (a.d <= 2) rwm_spec_kernel<2, TGT, RNG><<<g, 32, 0, stream()>>>(a);
@@ -562,7 +652,7 @@ static int rwm_launch_d(const RwmArgs &a) {
     return AMX_OK;
   }
   const unsigned grid = (unsigned)((a.nchains + kRwmThreads - 1) / kRwmThreads);
-  if constexpr (std::is_same<TGT, CoalTarget>::value) {
+  if constexpr (TargetIsWide<TGT>::value) {
     rwm_adapt_kernel<AMX_MAX_DIM, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);
   } else {
     if (a.d <= 2) rwm_adapt_kernel<2, TGT, RNG><<<grid, kRwmThreads, 0, stream()>>>(a);
@@ -580,6 +670,7 @@ static int rwm_launch(const amx_target *t, const RwmArgs &a) {
     case kTargetGaussMix: return rwm_launch_d<GaussMixTarget, RNG>(a);
     case kTargetQuad: return rwm_launch_d<QuadTarget, RNG>(a);
     case kTargetCoal: return rwm_launch_d<CoalTarget, RNG>(a);
+    case kTargetMixNorm: return rwm_launch_d<MixNormTarget, RNG>(a);
   }
   return fail(AMX_EINVAL, "plug-in kind %d has no device RWM kernel", t->d.kind);
 }
@@ -674,7 +765,16 @@ struct RwmJob {
   long nstore;
   int ntr;
   bool host_target;
+  // host callbacks through the mailbox: the kernel is in flight on `st` and must be served (mailbox_serve)
+  void *mb_host;
+  int mb_ncta, mb_nthr;
+  long mb_nexch;
+  cudaStream_t st;
 };
+static bool rwm_use_mailbox() {
+  const char *e = getenv("AMX_HOST_MAILBOX");
+  return !(e && atoi(e) == 0);
+}
 
 static int rwm_job_start(const amx_target *t, int model_k, int nsweep2, long nchains, const double *init,
                          uint64_t seed, const double *tape, long tape_stride, RwmJob &J) {
@@ -720,12 +820,35 @@ static int rwm_job_start(const amx_target *t, int model_k, int nsweep2, long nch
   AMX_CUDA(cudaEventCreate(&J.e0));
   AMX_CUDA(cudaEventCreate(&J.e1));
   AMX_CUDA(cudaEventRecord(J.e0, stream()));
-  int rc;
-  if (J.host_target) rc = rwm_host_run(t, a);
-  else rc = tape ? rwm_launch<TapeStream>(t, a) : rwm_launch<PhiloxStream>(t, a);
+  int rc = AMX_OK;
+  J.st = stream();
+  if (J.host_target && rwm_use_mailbox()) {
+    J.mb_nthr = nchains >= kMbThreads ? kMbThreads : (int)((nchains + 31) / 32 * 32);
+    J.mb_ncta = (int)((nchains + J.mb_nthr - 1) / J.mb_nthr);
+    J.mb_nexch = 1 + (long)a.nsweepr * d;
+    if ((rc = mailbox_alloc(&J.mb_host, J.mb_ncta, d))) return rc;
+    if (tape) rwm_mailbox_kernel<TapeStream><<<J.mb_ncta, J.mb_nthr, 0, stream()>>>(a, J.mb_host, d);
+    else rwm_mailbox_kernel<PhiloxStream><<<J.mb_ncta, J.mb_nthr, 0, stream()>>>(a, J.mb_host, d);
+    count_launch();
+    AMX_CUDA(cudaGetLastError());
+  } else if (J.host_target) {
+    rc = rwm_host_run(t, a);
+  } else {
+    rc = tape ? rwm_launch<TapeStream>(t, a) : rwm_launch<PhiloxStream>(t, a);
+  }
   if (rc) return rc;
   AMX_CUDA(cudaEventRecord(J.e1, stream()));
   return AMX_OK;
+}
+
+// answer the mailboxes of the jobs whose kernels wait for host log-posterior values (all of them at once: the models'
+// chains advance together, the callbacks run on this thread)
+static int rwm_jobs_serve(const amx_target *t, RwmJob *jobs, int n) {
+  std::vector<MbJob> mj;
+  for (int i = 0; i < n; i++)
+    if (jobs[i].mb_host) mj.push_back({jobs[i].mb_host, jobs[i].mb_ncta, jobs[i].a.d, jobs[i].mb_nthr, jobs[i].mb_nexch, jobs[i].st, 0u});
+  if (mj.empty()) return AMX_OK;
+  return mailbox_serve(mj, t->d);
 }
 
 static int rwm_job_finish(RwmJob &J, double *sig_out, double *samples_out, double *sig_trace0, double *acc_trace0,
@@ -746,6 +869,7 @@ static int rwm_job_finish(RwmJob &J, double *sig_out, double *samples_out, doubl
   cudaEventDestroy(J.e1);
   cudaFree(J.init_dev); cudaFree(J.gtab); cudaFree(J.tape_dev); cudaFree(J.sig_dev); cudaFree(J.samp_dev);
   cudaFree(J.tr_dev); cudaFree(J.status_dev);
+  if (J.mb_host) cudaFreeHost(J.mb_host);
   if (status & 1) return fail(AMX_ETAPE, "injected uniform tape exhausted");
   if (status & 2) return fail(AMX_ENUMERIC, "a chain reached a NaN log-posterior");
   return AMX_OK;
@@ -765,6 +889,7 @@ extern "C" int amx_rwm_adapt(const amx_target *t, int model_k, int nsweep2, long
     return fail(AMX_EINVAL, "amx_rwm_adapt: bad arguments");
   RwmJob J;
   if (int rc = rwm_job_start(t, model_k, nsweep2, nchains, init, seed, tape, tape_stride, J)) return rc;
+  if (int rc = rwm_jobs_serve(t, &J, 1)) return rc;
   return rwm_job_finish(J, sig_out, samples_out, sig_trace0, acc_trace0, kernel_ms);
 }
 
@@ -797,7 +922,7 @@ extern "C" int amx_rwm_adapt_all(const amx_target *t, int nsweep2, long nchains,
     off_s += (size_t)nchains * d;
     off_x += (size_t)nchains * 1000 * d * d;
   }
-  if (host) {  // callbacks run on the calling thread: one model after another
+  if (host && !rwm_use_mailbox()) {  // kernel-per-evaluation path: one model after another
     double tot = 0.0;
     for (int k = 0; k < nm && rc == AMX_OK; k++) {
       double ms = 0.0;
@@ -822,6 +947,7 @@ extern "C" int amx_rwm_adapt_all(const amx_target *t, int nsweep2, long nchains,
     if (rc == AMX_OK) started++;
   }
   amx_set_stream(saved);
+  if (rc == AMX_OK && host) rc = rwm_jobs_serve(t, jobs.data(), started);  // the models' kernels wait for values
   for (int k = 0; k < started; k++) {
     int r2 = rwm_job_finish(jobs[k], sig_out + os[k], samples_out + ox[k], sig_trace0 ? sig_trace0[k] : nullptr,
                             acc_trace0 ? acc_trace0[k] : nullptr, nullptr);

@@ -14,7 +14,7 @@
 
 namespace amx {
 
-enum TargetKind { kTargetGaussMix = 1, kTargetQuad = 2, kTargetCoal = 3, kTargetHostScalar = 100,
+enum TargetKind { kTargetGaussMix = 1, kTargetQuad = 2, kTargetCoal = 3, kTargetMixNorm = 4, kTargetHostScalar = 100,
                   kTargetHostBatched = 101 };
 
 // Solve T r = x - mu for the lower-triangular factor in a family record and return |r|^2.
@@ -204,6 +204,82 @@ struct CoalTarget {
       return lp + llh;
     }
   }
+};
+
+// ---- finite mixture of normals with an unknown number of components (BASELINE config 4) ------------------------
+// "Enzyme-style" data y_1..y_n; model k has K = ncomp[k] components and d = 3K - 1 parameters
+//   theta = (a_1 .. a_{K-1} | m_1 .. m_K | s_1 .. s_K):  stick-breaking logits, means, log standard deviations,
+//   w_j = v_j prod_{i<j} (1 - v_i), v_j = 1 / (1 + exp(-a_j)), w_K = prod_{i<K} (1 - v_i),
+//   log-likelihood sum_i log sum_j w_j N(y_i; m_j, exp(2 s_j)), independent normal priors (normalised, so that models of
+//   different dimension are comparable): a_j ~ N(0, pa^2), m_j ~ N(pm, pms^2), s_j ~ N(ps, pss^2).
+// The reference has no such example; the definition is ours, stated once in
+// automix_b200/workloads.py (c4_mixnorm) and restated for the host in oracle/host_targets.c.  Blob: amx_fam_hdr
+// (dims, ncomp) + [n, pa, pm, pms, ps, pss, y_1 .. y_n].
+constexpr int kMixNormKmax = 10;
+struct MixNormTarget {
+  const amx_fam_hdr *h;
+  const double *D;
+  __device__ __forceinline__ void bind(const void *blob, int) {
+    h = reinterpret_cast<const amx_fam_hdr *>(blob);
+    D = reinterpret_cast<const double *>(h + 1);
+  }
+  __device__ __forceinline__ int flops(int k) const { return (int)D[0] * (8 * h->ncomp[k] + 4) + 30 * h->ncomp[k]; }
+  static __device__ __forceinline__ double softplus(double x) {  // log(1 + exp(x)) without overflow
+    return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x));
+  }
+  template <int DMAX>
+  __device__ __forceinline__ double eval(int k, const double (&x)[DMAX]) const {
+    const int K = h->ncomp[k], n = (int)D[0];
+    const double pa = D[1], pm = D[2], pms = D[3], ps = D[4], pss = D[5];
+    const double *y = D + 6;
+    const double hl2pi = 0.9189385332046727;  // log(2 pi) / 2
+    double cj[kMixNormKmax], mj[kMixNormKmax], isj[kMixNormKmax];
+    double lrem = 0.0, lprior = 0.0;
+    for (int j = 0; j < K; j++) {
+      double lw = lrem;
+      if (j < K - 1) {
+        const double a = aget(x, j);
+        lw = lrem - softplus(-a);   // + log v_j
+        lrem -= softplus(a);        // + log (1 - v_j)
+        const double za = a / pa;
+        lprior += -0.5 * (za * za) - log(pa) - hl2pi;
+      }
+      const double m = aget(x, K - 1 + j), sl = aget(x, 2 * K - 1 + j);
+      const double zm = (m - pm) / pms, zs = (sl - ps) / pss;
+      lprior += (-0.5 * (zm * zm) - log(pms) - hl2pi) + (-0.5 * (zs * zs) - log(pss) - hl2pi);
+      cj[j] = lw - sl - hl2pi;
+      mj[j] = m;
+      isj[j] = exp(-sl);
+    }
+    double ll = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double yi = y[i];
+      double mx = -DBL_MAX, t[kMixNormKmax];
+      for (int j = 0; j < K; j++) {
+        const double z = (yi - mj[j]) * isj[j];
+        t[j] = cj[j] - 0.5 * (z * z);
+        mx = t[j] > mx ? t[j] : mx;
+      }
+      double ssum = 0.0;
+      for (int j = 0; j < K; j++) ssum += exp(t[j] - mx);
+      ll += mx + log(ssum);
+    }
+    return ll + lprior;
+  }
+};
+
+// Plug-ins whose models are wide (or whose evaluation is long): only the large kernel configurations are built for them.
+template <class TGT>
+struct TargetIsWide {
+  static constexpr bool value = false;
+};
+template <>
+struct TargetIsWide<CoalTarget> {
+  static constexpr bool value = true;
+};
+template <>
+struct TargetIsWide<MixNormTarget> {
+  static constexpr bool value = true;
 };
 
 // Host-side description of a plug-in (amx_api.cu owns these).

@@ -106,7 +106,11 @@ void sdrni(unsigned long *seed) {
   *seed = s;
 }
 
-double loggamma(double x) { return lgamma(x); }
+/* The reference's loggamma (Cody & Hillstrom's ALGAMA, automix.c:1323-1579) is defined for 0 < x <= XBIG and returns
+ * XINF = 1.79E308 for every other argument.  User log-posteriors lean on that: tests/test_automix.c:311-321 evaluates
+ * alpha * log(beta) - loggamma(alpha) with no support check, and it is the 1.79E308 that keeps the chain out of
+ * alpha <= 0 (lgamma is finite there). */
+double loggamma(double x) { return (x > 0.0 && x <= 2.55E305) ? lgamma(x) : 1.79E308; }
 
 /* ---- construction / destruction ---------------------------------------------------------------------- */
 static int alloc_proposal(proposalDist *jd, int nmodels, const int *dims, int Lcap) {
@@ -492,7 +496,7 @@ static int ensure_population(amSampler *am, sampler_ext *e, int n_trace) {
   if (tgt) {
     e->prop = amx_proposal_create(nm, jd->model_dims, jd->nMixComps, wt, mean, tri, sig);
     if (e->prop) {
-      long C = e->rj_chains > 0 ? e->rj_chains : env_long("AMX_CHAINS", e->user_target ? 65536 : 256);
+      long C = e->rj_chains > 0 ? e->rj_chains : env_long("AMX_CHAINS", e->user_target ? 65536 : 64);
       const uint64_t seed = e->seed_set ? e->seed : (uint64_t)am->seed;
       e->rj = amx_rj_create(e->prop, tgt, C, init, seed ^ 0x9E3779B97F4A7C15ull, n_trace);
       if (e->rj) {
@@ -558,7 +562,7 @@ void burn_samples(amSampler *am, int nburn) {
   const double t0 = wall_seconds();
   sampler_ext *e = ext_of(am, 1);
   if (!am->cpstats.isInitialized) estimate_conditional_probs(am, 100000); /* reference :137-139 */
-  if (!am->cpstats.isInitialized || unsupported_modes(am, e, "burn_samples")) return;
+  if (!am->cpstats.isInitialized || unsupported_modes(am, e, "burn_samples") || e->stats.last_error != 0) return;
   if (report(e, "population setup", ensure_population(am, e, 1))) return;
   amx_rj_set_modes(e->rj, am->student_T_dof, am->doPerm);
   if (nburn > 0) {
@@ -575,11 +579,12 @@ void rjmcmc_samples(amSampler *am, int nsweep) {
   runStats *st = &am->st;
   const int nm = am->jd.nmodels;
   if (!am->cpstats.isInitialized) estimate_conditional_probs(am, 100000); /* reference :79-81 */
-  if (!am->cpstats.isInitialized || unsupported_modes(am, e, "rjmcmc_samples") || nsweep < 1) return;
-  if (report(e, "population setup", ensure_population(am, e, 1))) return;
+  if (nsweep < 1) return;
   int dmax = 0;
   for (int k = 0; k < nm; k++)
     if (am->jd.model_dims[k] > dmax) dmax = am->jd.model_dims[k];
+  int setup_ok = am->cpstats.isInitialized && !unsupported_modes(am, e, "rjmcmc_samples") && e->stats.last_error == 0;
+  if (setup_ok && report(e, "population setup", ensure_population(am, e, 1))) setup_ok = 0;
 
   /* the reference re-creates its statistics on every call (initRunStats never sets
    * isInitialized, :357-394); keep that observable behaviour without its leak */
@@ -609,8 +614,20 @@ void rjmcmc_samples(amSampler *am, int nsweep) {
   st->theta_summary = (double ***)calloc(nm, sizeof(double **));
   e->st_alloc_nsweep = nsweep;
 
-  amx_rj_set_modes(e->rj, am->student_T_dof, am->doPerm);
-  if (report(e, "amx_rj_sweeps", amx_rj_sweeps(e->rj, nsweep, 0, am->doAdapt))) return;
+  if (setup_ok) amx_rj_set_modes(e->rj, am->student_T_dof, am->doPerm);
+  if (!setup_ok || report(e, "amx_rj_sweeps", amx_rj_sweeps(e->rj, nsweep, 0, am->doAdapt))) {
+    if (!setup_ok) fprintf(stderr, "automix-b200: rjmcmc_samples: an earlier stage failed (%s); no sweeps were run\n", amx_last_error());
+    /* The entry points are void (reference automix.h:86-100) and callers index am.st.theta_summary[k][i] right
+     * away: after a failed GPU stage leave every row pointing at zeros instead of NULL (the error has been printed
+     * and is in amx_sampler_stats.last_error). */
+    for (int k = 0; k < nm; k++) {
+      st->theta_summary[k] = (double **)malloc(sizeof(double *) * nsweep);
+      st->theta_summary[k][0] = (double *)calloc(dmax > 0 ? dmax : 1, sizeof(double));
+      for (int r = 1; r < nsweep; r++) st->theta_summary[k][r] = st->theta_summary[k][0];
+      st->theta_summary_size[k] = nsweep;
+    }
+    return;
+  }
   collect_population(e, nm);
   e->stats.sweeps_per_chain = (unsigned long long)nsweep;
 

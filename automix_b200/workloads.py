@@ -8,6 +8,7 @@ Target spec dicts:
   {"kind": "gaussmix", dims, ncomp, modw, wt, mean, tri, flags}
   {"kind": "quad", dims, center, scale, lo, hi}
   {"kind": "coalmine", dims}
+  {"kind": "mixnorm", dims, ncomp, y, prior}
 Proposal (mixture) dicts: {dims, ncomp, wt, mean, tri, sig}.
 """
 from __future__ import annotations
@@ -137,6 +138,39 @@ def coalmine():
     return dict(name="coalmine", target=dict(kind="coalmine", dims=dims), dims=dims,
                 init=np.concatenate(init),
                 thesis_probs=np.array([0.058, 0.250, 0.296, 0.234, 0.118, 0.044]))
+
+
+# --------------------------------------------------------------------------------------
+# C4: finite mixture of normals with an unknown number of components ("enzyme-style" data; not in the
+# reference -- SURVEY.md 8d gives the synthetic definition)
+# --------------------------------------------------------------------------------------
+def c4_mixnorm(nmodels: int = 10, n: int = 245, seed: int = 7):
+    """y_i, i = 1..245, from 0.6 N(0.19, 0.08^2) + 0.4 N(1.3, 0.5^2) (SplitMix64 stream `seed`: one uniform picks the
+    component, then one Box-Muller normal).  Model k (0-based) is a K = k+1 component normal mixture with
+    theta = (a_1..a_{K-1} | m_1..m_K | s_1..s_K): stick-breaking logits (w_j = v_j prod_{i<j}(1 - v_i), v = sigmoid(a)),
+    means, log standard deviations; d = 3K - 1 = 2, 5, ..., 29.  Normalised independent priors a ~ N(0, 1.5^2),
+    m ~ N(0.7, 1), s ~ N(log 0.3, 1); models a priori equally likely.  Start: equal weights, means spread over the
+    data's quantiles, log sd = log(sd(y) / K)."""
+    rng = SplitMix64(seed)
+    y = np.empty(n)
+    for i in range(n):
+        u = rng.uniform()
+        z = rng.normal()
+        y[i] = 0.19 + 0.08 * z if u < 0.6 else 1.3 + 0.5 * z
+    ncomp = np.arange(1, nmodels + 1, dtype=np.int32)
+    dims = (3 * ncomp - 1).astype(np.int32)
+    prior = np.array([1.5, 0.7, 1.0, math.log(0.3), 1.0])
+    ys = np.sort(y)
+    init = []
+    for K in ncomp:
+        K = int(K)
+        # stick-breaking logits of equal weights: v_j = 1 / (K - j)
+        a = [math.log((1.0 / (K - j)) / (1.0 - 1.0 / (K - j))) for j in range(K - 1)]
+        m = [float(ys[int((j + 0.5) / K * n)]) for j in range(K)]
+        s = [math.log(float(np.std(y)) / K)] * K
+        init.append(np.array(a + m + s))
+    return dict(name="c4_mixnorm", target=dict(kind="mixnorm", dims=dims, ncomp=ncomp, y=y, prior=prior), dims=dims,
+                init=np.concatenate(init), y=y)
 
 
 # --------------------------------------------------------------------------------------

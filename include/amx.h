@@ -107,6 +107,12 @@ amx_target *amx_target_quad(int nmodels, const int *dims, const double *center,
 /* Coal-mining change-point posterior (src/user_examples/usercpt.c:46-134),
  * models k=0..5, d=2k+3. */
 amx_target *amx_target_coalmine(void);
+/* Finite mixture of normals with an unknown number of components (BASELINE config 4, "enzyme-style" data): model k
+ * has ncomp[k] <= 10 components and d = 3 ncomp[k] - 1 parameters (stick-breaking logits | means | log standard
+ * deviations); y[ndata] are the observations; prior5 = (sd of the logits, mean and sd of the component means, mean and
+ * sd of the log standard deviations).  The reference ships no such example; the definition is in
+ * automix_b200/csrc/amx_targets.cuh (MixNormTarget) and automix_b200/workloads.py (c4_mixnorm). */
+amx_target *amx_target_mixnorm(int nmodels, const int *ncomp, int ndata, const double *y, const double *prior5);
 amx_target *amx_target_host_scalar(int nmodels, const int *dims,
                                    amx_scalar_fn f);
 amx_target *amx_target_host_batched(int nmodels, const int *dims,

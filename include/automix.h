@@ -193,7 +193,8 @@ typedef struct amx_sampler_stats {
  * does not take ownership of the plug-in. */
 int amx_sampler_set_target(amSampler *am, const struct amx_target *t);
 /* Population size for stage 3 (default: $AMX_CHAINS, else 65536 with a device plug-in and
- * 256 with a host callback) and number of independent stage-1 chains per model whose
+ * 64 with a host callback: up to there the callbacks hide behind the PCIe latency of an exchange,
+ * so the run costs what one chain would) and number of independent stage-1 chains per model whose
  * stored samples are pooled for the fit (default 1 = the reference's single chain). */
 int amx_sampler_set_chains(amSampler *am, long rj_chains, long rwm_chains);
 /* Seed of the counter-based per-chain streams (default: am->seed, which initAMSampler takes

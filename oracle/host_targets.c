@@ -20,7 +20,7 @@
 
 #include "amx_layout.h"
 
-enum { T_NONE = 0, T_GAUSSMIX, T_QUAD, T_COALMINE };
+enum { T_NONE = 0, T_GAUSSMIX, T_QUAD, T_COALMINE, T_MIXNORM };
 
 static int g_kind = T_NONE;
 static long g_calls = 0;
@@ -164,6 +164,63 @@ static double coal_eval(int k, const double *th) {
   return lp + llh;
 }
 
+/* --- finite mixture of normals, unknown number of components (BASELINE config 4) ------------
+ * Not in the reference; the definition is automix_b200/workloads.py:c4_mixnorm.  Model k has K = ncomp[k] components,
+ * theta = (a_1..a_{K-1} stick-breaking logits | m_1..m_K means | s_1..s_K log standard deviations). */
+#define MN_KMAX 10
+static int mn_nmodels = 0, mn_ncomp[AMX_MAX_MODELS], mn_n = 0;
+static double mn_prior[5], *mn_y = NULL;
+
+int amxh_select_mixnorm(int nmodels, const int *ncomp, int ndata, const double *y, const double *prior5) {
+  if (nmodels > AMX_MAX_MODELS) return -1;
+  mn_nmodels = nmodels;
+  for (int k = 0; k < nmodels; k++) mn_ncomp[k] = ncomp[k];
+  mn_n = ndata;
+  free(mn_y);
+  mn_y = malloc(sizeof(double) * ndata);
+  memcpy(mn_y, y, sizeof(double) * ndata);
+  memcpy(mn_prior, prior5, sizeof(mn_prior));
+  g_kind = T_MIXNORM;
+  return 0;
+}
+
+static double softplus(double x) { return x > 0.0 ? x + log1p(exp(-x)) : log1p(exp(x)); }
+
+static double mixnorm_eval(int k, const double *x) {
+  const int K = mn_ncomp[k];
+  const double pa = mn_prior[0], pm = mn_prior[1], pms = mn_prior[2], ps = mn_prior[3], pss = mn_prior[4];
+  const double hl2pi = 0.9189385332046727;
+  double cj[MN_KMAX], mj[MN_KMAX], isj[MN_KMAX], lrem = 0.0, lprior = 0.0;
+  for (int j = 0; j < K; j++) {
+    double lw = lrem;
+    if (j < K - 1) {
+      double a = x[j];
+      lw = lrem - softplus(-a);
+      lrem -= softplus(a);
+      double za = a / pa;
+      lprior += -0.5 * (za * za) - log(pa) - hl2pi;
+    }
+    double m = x[K - 1 + j], sl = x[2 * K - 1 + j];
+    double zm = (m - pm) / pms, zs = (sl - ps) / pss;
+    lprior += (-0.5 * (zm * zm) - log(pms) - hl2pi) + (-0.5 * (zs * zs) - log(pss) - hl2pi);
+    cj[j] = lw - sl - hl2pi;
+    mj[j] = m;
+    isj[j] = exp(-sl);
+  }
+  double ll = 0.0;
+  for (int i = 0; i < mn_n; i++) {
+    double mx = -DBL_MAX, t[MN_KMAX], ssum = 0.0;
+    for (int j = 0; j < K; j++) {
+      double z = (mn_y[i] - mj[j]) * isj[j];
+      t[j] = cj[j] - 0.5 * (z * z);
+      if (t[j] > mx) mx = t[j];
+    }
+    for (int j = 0; j < K; j++) ssum += exp(t[j] - mx);
+    ll += mx + log(ssum);
+  }
+  return ll + lprior;
+}
+
 /* --- the callbacks ---------------------------------------------------------- */
 double amxh_logpost(int k, double *x) {
   g_calls++;
@@ -171,6 +228,7 @@ double amxh_logpost(int k, double *x) {
     case T_GAUSSMIX: return gaussmix_eval(k, x);
     case T_QUAD: return quad_eval(k, x);
     case T_COALMINE: return coal_eval(k, x);
+    case T_MIXNORM: return mixnorm_eval(k, x);
   }
   return NAN;
 }

@@ -320,6 +320,7 @@ class HostTargets:
         L = self.lib
         L.amxh_select_gaussmix.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, C.c_int]
         L.amxh_select_quad.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp]
+        L.amxh_select_mixnorm.argtypes = [C.c_int, _ip, C.c_int, _dp, _dp]
         L.amxh_logpost.restype = C.c_double
         L.amxh_logpost.argtypes = [C.c_int, _dp]
         L.amxh_logpost_ptr.restype = C.c_void_p
@@ -344,6 +345,9 @@ class HostTargets:
                 _d(f64(lo)) if lo is not None else None, _d(f64(hi)) if hi is not None else None)
         elif kind == "coalmine":
             rc = self.lib.amxh_select_coalmine()
+        elif kind == "mixnorm":
+            rc = self.lib.amxh_select_mixnorm(len(spec["dims"]), _i(i32(spec["ncomp"])), len(spec["y"]),
+                                              _d(f64(spec["y"])), _d(f64(spec["prior"])))
         else:
             raise ValueError(kind)
         assert rc == 0

@@ -298,6 +298,7 @@ int main(void) {
   double u0 = sdrand();
   CHECK(fabs(u0 - 0.25515066366218653) < 1e-16, "sdrand after sdrni(12345) = %.17g", u0);
   CHECK(fabs(loggamma(7.25) - 7.0521854507385395) < 1e-13, "loggamma");
+  CHECK(loggamma(-1.5) == 1.79E308 && loggamma(0.0) == 1.79E308, "loggamma outside (0, XBIG] returns the reference's XINF");
 
   if (getenv("AMX_TEST_ONLY_COALMINE")) {
     test_coalmine();

@@ -84,7 +84,7 @@ def _fitted_proposal(amx, wl):
 
 
 @pytest.mark.parametrize("name,nchains,nsweeps", [("toy1", 64, 300), ("toy2", 48, 200), ("c5_rj", 40, 120), ("c1_normal", 33, 250), ("coalmine", 24, 150),
-                                                  ("coalmine_fitted", 24, 160)])
+                                                  ("coalmine_fitted", 24, 160), ("c4_mixnorm", 20, 80)])
 def test_population_against_oracle(amx, orc, ht, name, nchains, nsweeps):
     """Every chain gets its own tape; the oracle replays each chain on the CPU."""
     fitted = name.endswith("_fitted")
@@ -107,7 +107,7 @@ def test_population_against_oracle(amx, orc, ht, name, nchains, nsweeps):
         for d in dims:
             x0 = init[off:off + d]
             off += d
-            sc = np.maximum(np.abs(x0) * 0.15, 0.05) if name == "coalmine" else np.ones(d)
+            sc = np.maximum(np.abs(x0) * 0.15, 0.05) if name == "coalmine" else (np.full(d, 0.25) if name == "c4_mixnorm" else np.ones(d))
             L = 2
             ncomp.append(L)
             wt.append([0.6, 0.4])

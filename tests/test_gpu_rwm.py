@@ -15,7 +15,7 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))
 
 
-@pytest.mark.parametrize("name,k", [("toy1", 0), ("toy1", 1), ("toy2", 2), ("c1_normal", 0)])
+@pytest.mark.parametrize("name,k", [("toy1", 0), ("toy1", 1), ("toy2", 2), ("c1_normal", 0), ("c4_mixnorm", 1)])
 def test_chains_against_oracle(amx, orc, ht, name, k):
     wl = cases.workload(name)
     ptr = ht.select(wl["target"])
@@ -24,7 +24,7 @@ def test_chains_against_oracle(amx, orc, ht, name, k):
     init_all = cases.default_init(wl, 8)
     off = int(dims[:k].sum())
     init = init_all[off:off + d]
-    nchains, nsweep2 = 5, 1000
+    nchains, nsweep2 = (2 if name == "c4_mixnorm" else 5), 1000
     tlen = cases.rwm_tape_len(d, nsweep2)
     tapes = np.stack([cases.tape(300 + c, tlen) for c in range(nchains)])
     T = amx.Target(wl["target"])
@@ -109,7 +109,27 @@ def test_student_t_proposals_against_oracle(amx, orc, ht):
     amx.rwm_adapt(T, 0, 1000, 1, init[:1], dof=0)  # leave the process-wide setting at its default
 
 
-@pytest.mark.parametrize("name,k", [("toy1", 1), ("toy2", 3), ("coalmine", 2), ("coalmine", 5), ("c1_normal", 0)])
+def test_chain_of_dimension_29_against_oracle(amx, orc, ht):
+    """The widest model of BASELINE config 4 has d = 29: a stage-1 chain of that width (319 000 sweeps, 9.2e6
+    evaluations; separable quadratic target so that the oracle replays it in seconds) against the oracle."""
+    d = 29
+    spec = dict(kind="quad", dims=np.array([d], np.int32), center=np.linspace(-2, 2, d), scale=np.linspace(0.5, 3, d),
+                lo=None, hi=None)
+    ptr = ht.select(spec)
+    init = np.linspace(1, -1, d)
+    tape = cases.tape(29, cases.rwm_tape_len(d, 1000))[None, :]
+    r = amx.rwm_adapt(amx.Target(spec), 0, 1000, 1, init, tapes=tape)
+    orc.tape(tape[0])
+    o = orc.rwm_within_model(0, d, 1000, ptr, init)
+    assert r["samples"].shape == (1, 29000, 29)
+    rep_dev = np.all(r["samples"][0][1:] == r["samples"][0][:-1], axis=1)
+    rep_orc = np.all(o["samples"][1:] == o["samples"][:-1], axis=1)
+    assert np.array_equal(rep_dev, rep_orc), "accept pattern differs"
+    assert _rel(r["samples"][0], o["samples"]) < 1e-9 and _rel(r["sig"][0], o["sig"]) < 1e-9
+    assert _rel(r["sig_trace"][:5], o["sig_trace"][:5]) < 1e-12
+
+
+@pytest.mark.parametrize("name,k", [("toy1", 1), ("toy2", 3), ("coalmine", 2), ("coalmine", 5), ("c1_normal", 0), ("c4_mixnorm", 1)])
 def test_speculative_kernel_is_the_sequential_chain(amx, name, k, monkeypatch):
     """The warp-per-chain kernel (decision tree of the next five steps evaluated at once) and the
     thread-per-chain kernel run the same chain: bit-identical samples, scales and traces on Philox streams."""

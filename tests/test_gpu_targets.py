@@ -7,7 +7,7 @@ import cases
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["toy1", "toy2", "c5_rj", "c1_normal", "truncnormal", "coalmine"])
+@pytest.mark.parametrize("name", ["toy1", "toy2", "c5_rj", "c1_normal", "truncnormal", "coalmine", "c4_mixnorm"])
 def test_plugin_matches_host_callback(amx, ht, name):
     wl = cases.workload(name)
     spec = wl["target"]
@@ -24,6 +24,12 @@ def test_plugin_matches_host_callback(amx, ht, name):
         for i in range(n):
             x0 = wl["init"][offs[k[i]]:offs[k[i] + 1]]
             x[i, : dims[k[i]]] = x0 * (1 + 0.3 * rng.normal(size=dims[k[i]]))
+    elif name == "c4_mixnorm":  # around the start values and far out (logits +-40, log sds down to -8: softplus tails)
+        x = np.zeros((n, dmax))
+        offs = np.concatenate([[0], np.cumsum(dims)])
+        for i in range(n):
+            x0 = wl["init"][offs[k[i]]:offs[k[i] + 1]]
+            x[i, : dims[k[i]]] = x0 + rng.normal(size=dims[k[i]]) * (0.3 if i % 4 else 12.0)
     elif name == "c5_rj":
         x = rng.normal(size=(n, dmax)) * 2.5
     else:
