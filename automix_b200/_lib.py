@@ -32,7 +32,7 @@ class RjStats(C.Structure):
 
 class EmResult(C.Structure):
     _fields_ = [("L", C.c_int), ("iters", C.c_int), ("status", C.c_int), ("comp_steps", C.c_long),
-                ("kernel_ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+                ("kernel_ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double), ("bytes_requested", C.c_double)]
 
 
 _lib = None
@@ -448,7 +448,8 @@ def em_fit(x, init_idx, Lmax=30, maxit=5000, want_state=False, x_dev_ptr=None, d
     Lb, it = res.L, res.iters
     out = dict(L=Lb, iters=it, lam=wt[:Lb].copy(), mu=mean[:Lb].copy(), B=tri[:Lb].copy(), trace_L=trL[:it].copy(),
                trace_loglik=trll[:it].copy(), trace_cost=trc[:it].copy(), trace_ann=tra[:it].copy(),
-               kernel_ms=res.kernel_ms, comp_steps=res.comp_steps, flops=res.flops, bytes=res.bytes, status=res.status)
+               kernel_ms=res.kernel_ms, comp_steps=res.comp_steps, flops=res.flops, bytes=res.bytes,
+               bytes_requested=res.bytes_requested, status=res.status)
     if st:
         cl = int(st["cur_L"][0])
         out.update(cur_L=cl, cur_lam=st["cur_wt"][:cl].copy(), cur_mu=st["cur_mean"][:cl].copy(),

@@ -1633,7 +1633,11 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   int rc = AMX_OK;
 
   // peer access between all participants
-  if (ndev > 1)
+  // `devices` naming ONE GPU several times: the ranks are emulated by slices of a single grid on that GPU (the sharded
+  // exchange -- per-rank reduction, rows posted to every rank, sums in rank order -- exercised on a single-GPU box)
+  bool virt = ndev > 1;
+  for (int g = 1; g < ndev; g++) virt = virt && devs[g] == devs[0];
+  if (ndev > 1 && !virt)
     for (int g = 0; g < ndev; g++) {
       AMX_CUDA(cudaSetDevice(devs[g]));
       for (int h = 0; h < ndev; h++)
@@ -1726,6 +1730,14 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
     else if ((rc = em_occupancy_d(d, smem, &per_sm))) return rc;
     if (per_sm < 1) return fail(AMX_ECUDA, "EM kernel does not fit on an SM (%zu B of shared memory)", smem);
     long want = a.npad / kEmThreads, capb = (long)sms * per_sm;
+    if (virt) {  // the ranks share the GPU: equal slices of its SMs, the same number of CTAs for every rank
+      capb = sms / ndev;
+      for (int h = 0; h < ndev; h++) {
+        const long nh = off[h + 1] - off[h], th = (nh + kEmThreads - 1) / kEmThreads;
+        if (th < capb) capb = th;
+      }
+      if (capb < 1) return fail(AMX_EINVAL, "amx_em_fit_multi: too few samples for %d emulated ranks", ndev);
+    }
     unsigned grid = (unsigned)(want < capb ? want : capb);
     if (use_v2) {
       AMX_CUDA(ws_malloc(&v2sync[g], sizeof(V2Sync)));
@@ -1762,7 +1774,22 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   AMX_CUDA(cudaEventCreate(&e1));
   AMX_CUDA(cudaEventRecord(e0, st[0]));
   int launched = 0;
-  for (int g = 0; g < ndev && rc == AMX_OK; g++) {
+  EmArgs *va_dev = nullptr;
+  V2Args *vv_dev = nullptr;
+  if (virt) {
+    if (!use_v2) return fail(AMX_EINVAL, "emulated ranks on one GPU need the second-generation kernel (d <= %d)", kV2Dmax);
+    AMX_CUDA(ws_malloc(&va_dev, sizeof(EmArgs) * kEmMaxDev));
+    AMX_CUDA(ws_malloc(&vv_dev, sizeof(V2Args) * kEmMaxDev));
+    AMX_CUDA(cudaMemcpyAsync(va_dev, A, sizeof(EmArgs) * ndev, cudaMemcpyHostToDevice, st[0]));
+    AMX_CUDA(cudaMemcpyAsync(vv_dev, V, sizeof(V2Args) * ndev, cudaMemcpyHostToDevice, st[0]));
+    V2Args v0 = V[0];
+    v0.vranks = ndev;
+    v0.va = va_dev;
+    v0.vv = vv_dev;
+    rc = em2_launch(d, nteam, A[0], v0, (unsigned)(A[0].dev[0].grid * ndev), plan.smem, st[0]);
+    if (rc == AMX_OK) launched = 1;
+  }
+  for (int g = 0; g < ndev && rc == AMX_OK && !virt; g++) {
     cudaSetDevice(devs[g]);
     rc = use_v2 ? em2_launch(d, nteam, A[g], V[g], (unsigned)A[g].dev[g].grid, plan.smem, st[g])
                 : em_launch_d(d, A[g], (unsigned)A[g].dev[g].grid, smem, st[g]);
@@ -1833,6 +1860,7 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
       res->kernel_ms = ms;
       res->flops = c->flops;
       res->bytes = 8.0 * d * (double)n * (double)c->comp_steps;
+      res->bytes_requested = use_v2 ? c->s2 : 0.0;
     }
     if (getenv("AMX_EM_DEBUG") && use_v2) {
       V2Sync hs;
@@ -1867,6 +1895,8 @@ static int em_fit_general(int ndev, const int *devices, int d, long n, const dou
   }
   cudaSetDevice(devs[0]);
   ws_free(idx_dev);
+  ws_free(va_dev);
+  ws_free(vv_dev);
   ws_free(ctrl); ws_free(init_rows); ws_free(tr_L); ws_free(tr_ann); ws_free(tr_ll); ws_free(tr_cost);
   cudaSetDevice(home);
   if (rc != AMX_OK) return rc;

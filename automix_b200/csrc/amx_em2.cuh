@@ -42,6 +42,11 @@ struct V2Args {
   int ns;                                         // ring stages
   int region0_doubles;                            // ring / reduction scratch (aliased)
   int debug;
+  // Several ranks emulated by slices of ONE grid on one GPU (tests of the sharded exchange on a single-GPU box):
+  // CTAs [r gv, (r+1) gv) are rank r and take their argument blocks from these device arrays.
+  int vranks;
+  const EmArgs *va;
+  const V2Args *vv;
 };
 
 // Data layout in HBM (second generation): TILE-major.  The d coordinate rows of a 128-sample tile are contiguous
@@ -303,6 +308,12 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
     __syncwarp();
     return;
   }
+  // bytes this pass asked HBM for (all GPUs): the coordinate rows, the density rows it copied, the row(s) it wrote
+  if (lane == 0) {
+    const double nn = (double)a.n_total, Lp = (double)(S.L < 0 ? 0 : S.L);
+    S.tmp[kEmLmax - 1] += 8.0 * nn * (d + (pass == kPassRefresh0 ? 0.0 : Lp)) +
+                          8.0 * nn * (pass == kPassRefresh0 ? Lp : (pass == kPassDensRefresh ? 1.0 : 0.0));
+  }
   // a refresh finished: s_tot = [T_l (Lmax) | loglik | fallbacks | S1 (d) | S2 (tri)], column sums are lam_l T_l
   S.colsum[lane] = (lane < S.L) ? (S.keep ? s_tot[lane] : S.lam[lane] * s_tot[lane]) : 0.0;  // S.keep: a `direct` pass
   if (lane < d) S.S1[lane] = s_tot[kEmLmax + 2 + lane];
@@ -482,7 +493,15 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
 
 // ---- the kernel ----------------------------------------------------------------------------------------------
 template <int DMAX, int NTEAM>
-__global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2Args v) {
+__global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, V2Args v_in) {
+  EmArgs a = a_in;
+  V2Args v = v_in;
+  const int G = v_in.vranks > 1 ? (int)gridDim.x / v_in.vranks : (int)gridDim.x;  // CTAs of this rank
+  const int bid = (int)blockIdx.x % G;                                            // this CTA's index within its rank
+  if (v_in.vranks > 1) {
+    a = v_in.va[blockIdx.x / G];
+    v = v_in.vv[blockIdx.x / G];
+  }
   using CF = V2Cfg<DMAX>;
   constexpr int TRI = CF::TRI, NB = CF::NB, NE4 = CF::NE4;
   constexpr int NCONS = NTEAM * 128;
@@ -500,8 +519,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
   const int team = warp >> 2, wq = warp & 3, tt = t & 127;
   const long n = a.n, np = a.npad;
   const long ntiles = np / kV2TS;
-  const int G = (int)gridDim.x;
-  const bool writer = (a.rank == 0 && blockIdx.x == 0);
+  const bool writer = (a.rank == 0 && bid == 0);
   EmCtrl *ctrl = a.ctrl;
 
   // shared memory: [region0: ring, aliased by the end-of-pass reduction scratch][mu][B][rec][tot][part][LeaderS]
@@ -540,7 +558,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
 #pragma unroll
       for (int j = 0; j < 2 * DMAX; j++) acc[j] = 0.0;
       {
-        for (long i = (long)blockIdx.x * NCONS + t; i < n; i += (long)G * NCONS) {
+        for (long i = (long)bid * NCONS + t; i < n; i += (long)G * NCONS) {
 #pragma unroll
           for (int j = 0; j < DMAX; j++) {
             const double xv = a.x[i * d + j];
@@ -569,7 +587,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       const int L = S.L < 0 ? 0 : S.L, nx = S.next, cc = S.c;
       const bool dens_all = (pass == kPassRefresh0);  // first E-step: every density is formed here, unguarded weights
       const bool dens = (pass == kPassDensRefresh);
-      const int ntile_cta = (int)((ntiles - (long)blockIdx.x + G - 1) / G);  // tiles b, b+G, ... of this CTA
+      const int ntile_cta = (int)((ntiles - (long)bid + G - 1) / G);  // tiles b, b+G, ... of this CTA
       // Runs of consecutive live slots (the slot list is increasing: annihilation removes entries, never reorders):
       // run r covers components [s_run[2r], s_run[2r] + s_run[2r+1]).  The refreshed component's stale row is copied
       // with its run and overwritten in the stage (1 KB per tile, cheaper than splitting the run).
@@ -593,7 +611,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
         const unsigned long long seq = seq_base + (unsigned long long)it;
         const int st = (int)(seq % (unsigned)NS);
         double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS;
-        const long tl = (long)blockIdx.x + (long)it * G;
+        const long tl = (long)bid + (long)it * G;
         if (lane == 0) {
           s_gen[st] = (unsigned)(seq / (unsigned)NS) + 1u;  // fills issued for this stage
           mbar_expect_tx(&s_full[st], (uint32_t)(rows * kV2TS * 8));
@@ -629,7 +647,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
           const unsigned long long seq = seq_base + (unsigned long long)it;
           const int st = (int)(seq % (unsigned)NS);
           double *xs = ring + st * stage_doubles, *Es = xs + d * kV2TS, *winv = Es + Lmax * kV2TS;
-          const long tl = (long)blockIdx.x + (long)it * G;
+          const long tl = (long)bid + (long)it * G;
           const long i = tl * kV2TS + tt;
           const bool valid = i < n;
           // try_wait.parity can only tell the barrier's current phase from the one before it, so a team that runs
@@ -787,7 +805,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     // ------------------------------------------------------------------ exchange: partial rows -> totals everywhere
     const long long tk1 = clock64();
     V2Sync *me = v.sync[a.rank];
-    for (int q = t; q < nv; q += blockDim.x) __stcg(v.part + (size_t)q * G + blockIdx.x, s_part[q]);
+    for (int q = t; q < nv; q += blockDim.x) __stcg(v.part + (size_t)q * G + bid, s_part[q]);
     __syncthreads();
     if (t == 0) {
       __threadfence();
@@ -868,7 +886,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
     __syncthreads();
     const long long tk3 = clock64();
     dbg_pass += tk1 - tk0;
-    if (v.debug && t == 0) me->dbg_cta[blockIdx.x < 160 ? blockIdx.x : 159] = dbg_pass;
+    if (v.debug && t == 0) me->dbg_cta[bid < 160 ? bid : 159] = dbg_pass;
     dbg_bar += tk2 - tk1;
     dbg_lead += tk3 - tk2;
     pass = S.pass;
@@ -881,6 +899,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
       ctrl->pass = S.pass; ctrl->L = S.L; ctrl->c = S.c; ctrl->next = S.next; ctrl->iters = S.iters; ctrl->stop = S.stop;
       ctrl->status = S.status; ctrl->best_L = S.best_L; ctrl->comp_steps = S.comp_steps; ctrl->flops = S.flops;
       ctrl->loglik = S.loglik; ctrl->cost = S.cost; ctrl->cost_prev = S.cost_prev; ctrl->cost_best = S.cost_best;
+      ctrl->s2 = S.tmp[kEmLmax - 1];  // bytes requested (S.tmp's last entry is free: v2w_cost keeps its logs in registers)
       ctrl->dbg[0] = dbg_pass; ctrl->dbg[1] = dbg_bar; ctrl->dbg[3] = dbg_lead; ctrl->dbg[4] = dbg_x1; ctrl->dbg[5] = dbg_x2;
     }
     const int Lw = S.L < 0 ? 0 : S.L;
@@ -894,7 +913,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a, V2A
   // optional dump of the responsibilities of the working state (step-parity tests)
   if (a.w_out != nullptr) {
     const int L = S.L;
-    for (long i = (long)blockIdx.x * blockDim.x + t; i < n; i += (long)G * blockDim.x) {
+    for (long i = (long)bid * blockDim.x + t; i < n; i += (long)G * blockDim.x) {
       double sum = 0.0;
       for (int l = 0; l < L; l++) sum += S.lam[l] * __ldcg(a.E + v2_e_at(i, S.slot[l], Lmax));
       for (int l = 0; l < L; l++) {

@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--em-steps", type=int, default=3)
     ap.add_argument("--no-em", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sweep kernel's coal-mining / 10-model legs")
     ap.add_argument("--workload", default="toy1", choices=["toy1", "toy2", "c5_rj", "c1_normal"])
     return ap.parse_args()
 
@@ -68,6 +69,19 @@ def workload(args):
                    mean=np.array([0.5]), tri=np.array([1.05]), sig=np.array([4.9]))
         init, desc = wl["init"], "proposal = the mixture the reference fits (SURVEY.md appendix C)"
     return wl, mix, np.asarray(init, np.float64), desc
+
+
+def ncu_record(kind):
+    """DRAM traffic and pipe utilisation of the dominant kernels come from ncu, which cannot run inside a timed bench:
+    they are read from the committed summary of the round's capture (profiles/ncu_latest.json, written from the .ncu-rep
+    by profiles/summarize_r02.py) and attached WITH their source and configuration; absent file -> None."""
+    path = os.path.join(ROOT, "profiles", "ncu_latest.json")
+    if not os.path.exists(path):
+        return None
+    try:
+        return json.load(open(path)).get(kind)
+    except (OSError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -146,8 +160,8 @@ def run_reference(args):
             "e2e": {"value": value, "unit": "chain-sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if not args.no_em:
-        x, _ = W.c5_em_samples(n=20000, d=args.em_d, seed=2025)
-        e = cpu_bench.em_baseline(x, args.em_L, 0)
+        x = W.c5_em_samples(n=args.em_n, d=args.em_d, seed=2025)[0][:100000]
+        e = cpu_bench.em_baseline(x, args.em_L, 2)
         line["em"] = {"metric": "EM-fit samples/s", "value": e["value"], "unit": "EM-fit samples/s",
                       "cpu_baseline": {k: e[k] for k in ("value", "unit", "cores", "kind", "sample")}}
     print(json.dumps(line), flush=True)
@@ -234,10 +248,11 @@ def main():
         ach = float(st["flops"]) / (st["kernel_ms"] * 1e-3)  # this rank's dominant kernel, per-launch average
         roof_rj = {"bound": "fp64", "achieved": ach / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                    "frac": ach / fp64_peak,
-                   # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^20 chains (state load/store
-                   # only; independent of the number of sweeps): profiles/r01/ncu_rj_r01f.txt (67.2 + 19.1 MB)
-                   "traffic": 86.3e6 * (C / float(1 << 20)),
-                   "fp64_pipe_active_pct_ncu": 27.3,
+                   # chain state is loaded once and stored once per launch, whatever the number of sweeps: the bytes the
+                   # kernel asks for; "traffic" is ncu's DRAM count of the same launch shape when a capture is committed
+                   "requested_bytes": float(2 * C * (8 * (int(mix["dims"].max()) + nm + 2) + 16)),
+                   "traffic": (lambda q: (q["dram_bytes_per_launch"] * C / q["chains"]) if q else None)(ncu_record("rj")),
+                   "ncu": ncu_record("rj"),
                    "kernel": "rj_sweep_kernel", "launch_ms": st["kernel_ms"] / args.steps,
                    "flops_per_sweep": float(st["flops"]) / (C * S * args.steps),
                    "peak_source": "measured live with amx_measure_fp64_peak (dependent-free DFMA loop); "
@@ -295,6 +310,35 @@ def main():
     pop.close()
     del flush
 
+    # ------------------------------------------------------------------ the sweep kernel on the wider configurations
+    # (BASELINE configs 3 and 5: coal-mining change points, d = 3..13, on the proposal the reference fitted; ten
+    # synthetic multimodal Gaussian models, d = 2..20); device-resident, library CUDA events around the launches
+    k3_other = None
+    if rank == 0 and not args.no_extra:
+        k3_other = {}
+        for name, chains, sw in (("c5_rj", 1 << 16, 100), ("coalmine", 1 << 16, 200)):
+            wl2 = getattr(W, name)()
+            if name == "coalmine":
+                g2 = np.load(os.path.join(ROOT, "tests", "golden", "coalmine_posterior.npz"))
+                mix2 = {k[4:]: g2[k] for k in g2.files if k.startswith("mix_")}
+            else:
+                mix2 = W.ideal_proposal(wl2)
+            T2, P2 = amx.Target(wl2["target"]), amx.Proposal(mix2)
+            pop2 = amx.RjPopulation(P2, T2, chains, wl2["init"], seed=7)
+            pop2.init_chains()
+            pop2.sweeps(100, burning=True)
+            pop2.collect(reset=True)
+            for _ in range(3):
+                pop2.sweeps(sw)
+            vis2, st2 = pop2.collect()
+            secs = st2["kernel_ms"] * 1e-3
+            k3_other[name] = {"value": 3.0 * chains * sw / secs, "unit": "chain-sweeps/s", "chains": chains,
+                              "sweeps_per_launch": sw, "ms_per_launch": 1e3 * secs / 3,
+                              "flops_per_sweep": float(st2["flops"]) / (3.0 * chains * sw),
+                              "fp64_frac": float(st2["flops"]) / secs / fp64_peak if fp64_peak else None,
+                              "model_probs": (vis2 / vis2.sum()).round(4).tolist()}
+            pop2.close()
+
     # ------------------------------------------------------------------ EM fit (second metric)
     em = None
     if not args.no_em and rank == 0:
@@ -319,11 +363,24 @@ def main():
         alg_bytes = 8.0 * d * n * steps_
         stream_bytes = 8.0 * n * steps_ * (2 * d + L + 3)  # upper bound of what the two passes move (L = Lmax)
         amx.em_fit(x_pin.numpy(), idx, Lmax=L, maxit=args.em_maxit)  # untimed warm-up of the host-buffer path
-        t0 = time.perf_counter()
-        e2e_fits = 2
+        e2e_fits, t_e2e_all, k_e2e = 3, [], []
         for _ in range(e2e_fits):
+            t0 = time.perf_counter()
             r2 = amx.em_fit(x_pin.numpy(), idx, Lmax=L, maxit=args.em_maxit)  # H2D of x inside
-        t_e2e = (time.perf_counter() - t0) / e2e_fits
+            t_e2e_all.append(time.perf_counter() - t0)
+            k_e2e.append(r2["kernel_ms"] * 1e-3)
+        t_e2e = float(np.mean(t_e2e_all))
+        # where an end-to-end fit goes: the upload alone (same pinned buffer, CUDA events), the kernel, the rest
+        # (workspace from the pool, start rows, result read-back, host bookkeeping)
+        eu0, eu1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eu0.record(stream)
+        x_dev.copy_(x_pin, non_blocking=True)
+        eu1.record(stream)
+        torch.cuda.synchronize()
+        h2d_s = eu0.elapsed_time(eu1) * 1e-3
+        e2e_breakdown = {"h2d_ms": 1e3 * h2d_s, "kernel_ms": 1e3 * float(np.mean(k_e2e)),
+                         "other_ms": 1e3 * (t_e2e - h2d_s - float(np.mean(k_e2e))), "total_ms": 1e3 * t_e2e,
+                         "per_fit_ms": [round(1e3 * v, 2) for v in t_e2e_all]}
         em_multi = None
         if world > 1:
             # the same fit with the samples sharded over all N GPUs of the box (strong scaling: n fixed); rank 0
@@ -335,8 +392,15 @@ def main():
                 rm = amx.em_fit(x, idx, Lmax=L, maxit=args.em_maxit, devices=devs)
                 tms.append(rm["kernel_ms"])
             tm_fit = float(np.mean(tms)) * 1e-3
+            def _rel(a, b):
+                a, b = np.asarray(a, float), np.asarray(b, float)
+                return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+            same = bool(np.array_equal(rm["trace_L"], r["trace_L"]) and np.array_equal(rm["trace_ann"], r["trace_ann"]))
+            dev_par = max(_rel(rm["lam"], r["lam"]), _rel(rm["mu"], r["mu"]), _rel(rm["B"], r["B"]),
+                          _rel(rm["trace_loglik"], r["trace_loglik"])) if same and rm["L"] == r["L"] else float("inf")
+            assert same and dev_par < 1e-10, ("sharded fit differs from the single-GPU fit", same, dev_par)
             em_multi = {"n_gpus": world, "scaling": "strong", "value": n * rm["iters"] / tm_fit, "ms_per_fit": 1e3 * tm_fit,
-                        "same_trace_as_single_gpu": bool(np.array_equal(rm["trace_L"], r["trace_L"])),
+                        "same_trace_as_single_gpu": same, "max_rel_dev_of_lam_mu_B_loglik_vs_single_gpu": dev_par,
                         "exchange": "per pass <= 2 KB per GPU through NVLink peer memory inside the kernel, fixed GPU order"}
         em = {"metric": "EM-fit samples/s", "value": n * its / t_fit, "unit": "EM-fit samples/s",
               "ms_per_fit": 1e3 * t_fit, "outer_iterations": its, "component_steps": int(steps_),
@@ -346,18 +410,23 @@ def main():
                                      "inputs (80 MB) + density cache (240 MB) exceed L2, no flush needed"},
               "roofline": {"bound": "hbm", "achieved": alg_bytes / t_fit / 1e9, "peak": hbm, "unit": "GB/s",
                            "frac": alg_bytes / t_fit / 1e9 / hbm,
-                           # ncu: 21.58 GB (read+write) for 74 component steps + start-up at n=1e6, d=10, L=30 with the
-                           # fused step (profiles/r01/ncu_em_r01f.txt) -> 0.292 GB per component step, scaled to
-                           # this launch by the rows a step streams (x, density cache, weights)
-                           "traffic": 0.292e9 * steps_ * (n / 1e6) * ((d + L + 2) / 42.0),
-                           "kernel": "em_fit_kernel", "launch_ms": 1e3 * t_fit,
+                           # bytes the kernel itself asked HBM for, summed over its passes by the kernel (rows copied into
+                           # the ring + rows written); "traffic" is ncu's DRAM count per launch when a capture of this
+                           # launch shape is committed (scaled by component steps)
+                           "requested_bytes": float(r["bytes_requested"]),
+                           "traffic": (lambda q: (q["dram_bytes_per_component_step"] * steps_)
+                                       if q and q.get("n") == n and q.get("d") == d and q.get("Lmax") == L else None)(ncu_record("em")),
+                           "ncu": ncu_record("em"),
+                           "kernel": "em_fit_v2_kernel", "launch_ms": 1e3 * t_fit,
+                           "requested_GBs": float(r["bytes_requested"]) / t_fit / 1e9,
+                           "requested_frac_of_peak": float(r["bytes_requested"]) / t_fit / 1e9 / hbm,
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                            "note": "algorithmic bytes = 8 d per sample-component-step (SURVEY.md 8d)",
                            "streamed_model_GBs": stream_bytes / t_fit / 1e9,
                            "fp64": {"achieved": r["flops"] / t_fit / 1e12, "peak": fp64_peak / 1e12,
                                     "frac": r["flops"] / t_fit / fp64_peak, "unit": "TFLOP/s",
                                     "note": "F_EM = 2d^2+8d+4L+7 flops per sample-component-step"}},
-              "e2e": {"value": n * r2["iters"] / t_e2e, "unit": "EM-fit samples/s",
+              "e2e": {"value": n * r2["iters"] / t_e2e, "unit": "EM-fit samples/s", "breakdown": e2e_breakdown,
                       "h2d_bytes_per_step": int(x.nbytes + 4 * L), "d2h_bytes_per_step": int(8 * L * (1 + d + d * (d + 1) // 2) + 24 * its)},
               "gpu_launches": int(em_launches)}
         if em_multi is not None:
@@ -372,8 +441,10 @@ def main():
 
         cpu = cpu_bench.rj_baseline(wl["target"], mix, init, 10000, 4_000_000)
         if em is not None:
-            xs, _ = W.c5_em_samples(n=20000, d=args.em_d, seed=2025)
-            e = cpu_bench.em_baseline(xs, args.em_L, 1)
+            # the identical sample array; bounded to its first 1e5 samples and NUM_FITMIX_MAX = 2
+            # (three outer iterations: ~10-20 s per core)
+            xs = W.c5_em_samples(n=args.em_n, d=args.em_d, seed=2025)[0][:100000]
+            e = cpu_bench.em_baseline(xs, args.em_L, 2)
             em["cpu_baseline"] = {k: e[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -394,6 +465,8 @@ def main():
             line["cpu_baseline"]["per_core"] = cpu["per_core"]
         if em is not None:
             line["em"] = em
+        if k3_other is not None:
+            line["rj_other_workloads"] = k3_other
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

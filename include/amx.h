@@ -246,6 +246,8 @@ typedef struct amx_em_result {
   double kernel_ms; /* device time of the fit kernel */
   double flops;     /* F_EM of SURVEY.md 8d, summed over component steps */
   double bytes;     /* 8*d bytes per sample-component-step, summed */
+  double bytes_requested; /* what the kernel itself asked HBM for: rows copied into the ring + rows written, summed over
+                             the passes by the kernel (0 from the first-generation kernel) */
 } amx_em_result;
 
 /*

@@ -101,6 +101,32 @@ def test_shapes_against_oracle(amx, orc, d, n, L):
     assert np.max(np.abs(r["cur_w"] - o["cur_w"])) < 1e-11
 
 
+@pytest.mark.parametrize("n,maxit", [(100_000, 1), (1_000_000, 0)])
+def test_benchmark_configuration_against_oracle(amx, orc, n, maxit):
+    """The headline EM configuration itself (C5-EM: d = 10, Lmax = 30, the bench's sample array) against the oracle:
+    the first outer iterations -- 30 resp. 60 component steps with their annihilations -- at the per-step bar.
+    (One outer iteration of the oracle costs ~5 s per 1e5 samples on a host core, which bounds how far this can go.)"""
+    from automix_b200 import workloads as W
+
+    x = W.c5_em_samples(n=1_000_000, d=10, G=6, seed=2025)[0][:n]
+    orc.tape(cases.tape(99, 4096))
+    o = orc.fit_mixture(x, Lmax=30, maxit=maxit, want_state=True)
+    r = amx.em_fit(x, o["init_idx"], Lmax=30, maxit=maxit, want_state=True)
+    assert r["iters"] == o["iters"] == maxit + 1 and r["cur_L"] == o["cur_L"]
+    assert np.array_equal(r["trace_L"], o["trace_L"]) and np.array_equal(r["trace_ann"], o["trace_ann"])
+    # The reference (and the oracle) add their 1e6 terms one after the other: a sum of n fp64 terms formed that way is
+    # itself only good to ~sqrt(n) 2^-53 relative (2e-13 at 1e5, 1e-12 at 1e6, more where terms cancel), while the kernel
+    # adds them as a tree.  The per-step bar holds at 1e5; at 1e6 the bound is the reference's own summation error.
+    tol = STEP_RTOL if n <= 100_000 else 2e-11
+    assert _rel(r["trace_loglik"], o["trace_loglik"]) < tol
+    assert _rel(r["trace_cost"], o["trace_cost"]) < tol
+    assert _rel(r["cur_lam"], o["cur_lam"]) < tol
+    assert _rel(r["cur_mu"], o["cur_mu"]) < tol
+    assert _rel(r["cur_B"], o["cur_B"]) < tol
+    assert np.max(np.abs(r["cur_w"] - o["cur_w"])) < tol
+    assert r["bytes_requested"] > r["bytes"] > 0
+
+
 def test_fit_is_invariant_to_sample_order_at_full_size(amx):
     """Size-independent property at n = 2^20: the fitted mixture does not depend on the order of
     the samples (sums are order-free up to rounding) when the same rows start the components."""
