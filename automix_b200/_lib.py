@@ -41,7 +41,7 @@ _lib = None
 EXPORTS = [
     "amx_last_error", "amx_version", "amx_device_count", "amx_set_device", "amx_set_stream",
     "amx_synchronize", "amx_set_deferred_sync", "amx_release_workspace", "amx_launch_count", "amx_measure_fp64_peak", "amx_mix_logpdf",
-    "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine", "amx_target_mixnorm",
+    "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine", "amx_target_mixnorm", "amx_target_plugin",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
     "amx_rj_set_tape", "amx_rj_set_pk_mode", "amx_rj_get_pk_shared", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
@@ -80,6 +80,8 @@ def lib():
     L.amx_target_quad.restype = C.c_void_p
     L.amx_target_quad.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp]
     L.amx_target_coalmine.restype = C.c_void_p
+    L.amx_target_plugin.restype = C.c_void_p
+    L.amx_target_plugin.argtypes = [C.c_char_p, C.c_int, _ip, C.c_void_p, C.c_size_t, C.c_int]
     L.amx_target_mixnorm.restype = C.c_void_p
     L.amx_target_mixnorm.argtypes = [C.c_int, _ip, C.c_int, _dp, _dp]
     L.amx_target_host_scalar.restype = C.c_void_p
@@ -214,6 +216,11 @@ class Target:
                                        _d(f64(hi)) if hi is not None else None)
         elif kind == "coalmine":
             self.h = L.amx_target_coalmine()
+        elif kind == "plugin":  # {"kind": "plugin", "so": path, "dims": ..., "blob": bytes-like, "flags": int}
+            blob = np.frombuffer(bytes(spec.get("blob", b"")), dtype=np.uint8)
+            self._blob = blob
+            self.h = L.amx_target_plugin(str(spec["so"]).encode(), len(self.dims), _i(self.dims),
+                                         blob.ctypes.data_as(C.c_void_p) if len(blob) else None, len(blob), int(spec.get("flags", 0)))
         elif kind == "mixnorm":
             self.h = L.amx_target_mixnorm(len(self.dims), _i(i32(spec["ncomp"])), len(spec["y"]), _d(f64(spec["y"])),
                                           _d(f64(spec["prior"])))
@@ -400,6 +407,29 @@ class RjPopulation:
             self.close()
         except Exception:
             pass
+
+
+class FamHdr(C.Structure):
+    """amx_fam_hdr of include/amx_layout.h."""
+    _fields_ = [("nmodels", C.c_int), ("dmax", C.c_int), ("Lmax", C.c_int), ("total", C.c_int)] + [
+        (n, C.c_int * 32) for n in ("dims", "ncomp", "off", "stride", "ext", "extlen")]
+
+
+def family_blob(spec) -> bytes:
+    """The device family blob [amx_fam_hdr | doubles] of a Gaussian-mixture target spec (amx_fam_plan + amx_fam_pack with
+    AMX_FAM_TARGET): the parameter block a user plug-in for such a target receives in bind()."""
+    L = lib()
+    L.amx_fam_plan.argtypes = [C.POINTER(FamHdr), C.c_int, _ip, _ip, _ip]
+    L.amx_fam_pack.argtypes = [C.POINTER(FamHdr), C.c_int, _dp, _dp, _dp, _dp, _dp]
+    h = FamHdr()
+    dims, ncomp = i32(spec["dims"]), i32(spec["ncomp"])
+    ext = np.ones(len(dims), np.int32)
+    total = L.amx_fam_plan(C.byref(h), len(dims), _i(dims), _i(ncomp), _i(ext))
+    if total < 0:
+        raise AmxError("bad family shape")
+    data = np.zeros(total)
+    L.amx_fam_pack(C.byref(h), 1, _d(f64(spec["wt"])), _d(f64(spec["mean"])), _d(f64(spec["tri"])), _d(f64(spec["modw"])), _d(data))
+    return bytes(h) + data.tobytes()
 
 
 def em_draw_init(n, Lmax, uniforms):

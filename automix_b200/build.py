@@ -27,7 +27,7 @@ CFLAGS = ["-O2", "-fPIC", "-Wall", "-I", INC, "-I", CSRC]
 
 
 def _sources():
-    cu = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    cu = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and f != "amx_plugin_tu.cu")  # (the plug-in TU is built per plug-in)
     c = sorted(f for f in os.listdir(CSRC) if f.endswith(".c"))
     return cu, c
 

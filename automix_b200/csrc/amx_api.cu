@@ -8,6 +8,8 @@
 #include <vector>
 
 #include "amx_common.cuh"
+#include <dlfcn.h>
+
 #include "amx_internal.cuh"
 #include "amx_targets.cuh"
 
@@ -246,6 +248,47 @@ amx_target *amx_target_mixnorm(int nmodels, const int *ncomp, int ndata, const d
   return t;
 }
 
+amx_target *amx_target_plugin(const char *so_path, int nmodels, const int *dims, const void *blob, size_t blob_bytes,
+                              int flags) {
+  if (require_device()) return nullptr;
+  if (!so_path || nmodels < 1 || nmodels > AMX_MAX_MODELS || !dims || (blob_bytes && !blob) || (blob_bytes & 7)) {
+    fail(AMX_EINVAL, "amx_target_plugin: bad arguments (the parameter blob must be a multiple of 8 bytes)");
+    return nullptr;
+  }
+  void *dl = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+  if (!dl) {
+    fail(AMX_EINVAL, "amx_target_plugin: %s", dlerror());
+    return nullptr;
+  }
+  typedef const PluginVtbl *(*entry_fn)(void);
+  entry_fn entry = (entry_fn)dlsym(dl, "amx_plugin_entry");
+  const PluginVtbl *v = entry ? entry() : nullptr;
+  if (!v || v->abi != kPluginAbi) {
+    fail(AMX_EINVAL, "amx_target_plugin: %s is not a plug-in of this library version (rebuild it with python -m automix_b200.plugin)", so_path);
+    dlclose(dl);
+    return nullptr;
+  }
+  amx_target *t = new_target(kTargetPlugin, nmodels, dims);
+  if (!t) {
+    dlclose(dl);
+    return nullptr;
+  }
+  t->d.plugin = v;
+  t->d.plugin_dl = dl;
+  t->d.flags = flags;
+  const size_t nb = blob_bytes ? blob_bytes : 8;
+  if (cudaMalloc(&t->d.blob_dev, nb) != cudaSuccess ||
+      (blob_bytes && cudaMemcpy(t->d.blob_dev, blob, blob_bytes, cudaMemcpyHostToDevice) != cudaSuccess)) {
+    fail(AMX_ECUDA, "amx_target_plugin: parameter upload failed");
+    if (t->d.blob_dev) cudaFree(t->d.blob_dev);
+    dlclose(dl);
+    free(t);
+    return nullptr;
+  }
+  t->d.blob_bytes = (int)blob_bytes;
+  return t;
+}
+
 amx_target *amx_target_host_scalar(int nmodels, const int *dims, amx_scalar_fn f) {
   amx_target *t = new_target(kTargetHostScalar, nmodels, dims);
   if (t) t->d.scalar = f;
@@ -262,6 +305,7 @@ amx_target *amx_target_host_batched(int nmodels, const int *dims, amx_batched_fn
 void amx_target_destroy(amx_target *t) {
   if (!t) return;
   if (t->d.blob_dev) cudaFree(t->d.blob_dev);
+  if (t->d.plugin_dl) dlclose(t->d.plugin_dl);
   free(t);
 }
 

@@ -14,7 +14,7 @@
 
 namespace amx {
 
-enum TargetKind { kTargetGaussMix = 1, kTargetQuad = 2, kTargetCoal = 3, kTargetMixNorm = 4, kTargetHostScalar = 100,
+enum TargetKind { kTargetGaussMix = 1, kTargetQuad = 2, kTargetCoal = 3, kTargetMixNorm = 4, kTargetPlugin = 50, kTargetHostScalar = 100,
                   kTargetHostBatched = 101 };
 
 // Solve T r = x - mu for the lower-triangular factor in a family record and return |r|^2.
@@ -282,8 +282,25 @@ struct TargetIsWide<MixNormTarget> {
   static constexpr bool value = true;
 };
 
+// A user-supplied __device__ log-posterior: a shared object built from the user's source and amx_plugin_tu.cu
+// (python -m automix_b200.plugin), holding the K1/K3 kernels instantiated for the user's struct, reached through this
+// table (amx_target_plugin, include/amx.h).
+struct RjLaunch;
+struct RwmArgs;
+constexpr int kPluginAbi = 2;
+struct PluginVtbl {
+  int abi;
+  int (*rj_sweeps)(const RjLaunch *a, int dmax, int Lmax, int nm, int tape);
+  int (*rj_init)(const RjLaunch *a, const double *init_dev, int tape);
+  int (*rwm)(const RwmArgs *a, int tape);
+  int (*eval)(const void *blob_dev, int flags, const int *dims, long n, const int *k_dev, const double *x_dev, long ldx,
+              double *out_dev);
+};
+
 // Host-side description of a plug-in (amx_api.cu owns these).
 struct TargetDesc {
+  const PluginVtbl *plugin;  // kTargetPlugin
+  void *plugin_dl;
   int kind;
   int flags;
   int nmodels;

@@ -113,6 +113,15 @@ amx_target *amx_target_coalmine(void);
  * sd of the log standard deviations).  The reference ships no such example; the definition is in
  * automix_b200/csrc/amx_targets.cuh (MixNormTarget) and automix_b200/workloads.py (c4_mixnorm). */
 amx_target *amx_target_mixnorm(int nmodels, const int *ncomp, int ndata, const double *y, const double *prior5);
+/* A USER-SUPPLIED __device__ log-posterior: the device variant of the reference's `double f(int model_k, double *x)`.
+ * The user writes a CUDA header defining `struct AmxUserTarget { bind(blob, flags); flops(k); template <int DMAX>
+ * double eval(k, const double (&x)[DMAX]); }` (see automix_b200/csrc/amx_plugin_tu.cu and tests/plugins/toy1_user.cuh),
+ * builds it once with `python -m automix_b200.plugin build my_target.cuh` (nvcc; the same kernel templates the built-in
+ * families use are instantiated for it: full speed, chain state on-chip for all sweeps), and hands the resulting shared
+ * object here with the models' dimensions and an opaque parameter blob (a multiple of 8 bytes; bind() receives it).
+ * Everything that takes an amx_target -- amx_rwm_adapt, amx_rj_*, amx_target_eval, amx_sampler_set_target -- accepts it. */
+amx_target *amx_target_plugin(const char *so_path, int nmodels, const int *dims, const void *blob, size_t blob_bytes,
+                              int flags);
 amx_target *amx_target_host_scalar(int nmodels, const int *dims,
                                    amx_scalar_fn f);
 amx_target *amx_target_host_batched(int nmodels, const int *dims,
