@@ -494,13 +494,20 @@ __device__ void v2_leader_warp(const EmArgs &a, EmCtrl *c, bool writer, int pass
 // ---- the kernel ----------------------------------------------------------------------------------------------
 template <int DMAX, int NTEAM>
 __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, V2Args v_in) {
-  EmArgs a = a_in;
-  V2Args v = v_in;
+  // (the argument blocks stay in parameter space -- constant-bank operands; only what differs between emulated ranks is
+  // taken from the device arrays, into registers)
+  const EmArgs &a = a_in;
+  const V2Args &v = v_in;
   const int G = v_in.vranks > 1 ? (int)gridDim.x / v_in.vranks : (int)gridDim.x;  // CTAs of this rank
   const int bid = (int)blockIdx.x % G;                                            // this CTA's index within its rank
+  int rk_rank = a_in.rank;
+  long rk_n = a_in.n, rk_npad = a_in.npad;
+  const double *rk_x = a_in.x;
+  double *rk_xT = a_in.xT, *rk_E = a_in.E, *rk_wout = a_in.w_out, *rk_part = v_in.part;
   if (v_in.vranks > 1) {
-    a = v_in.va[blockIdx.x / G];
-    v = v_in.vv[blockIdx.x / G];
+    const EmArgs *ra = v_in.va + blockIdx.x / G;
+    rk_rank = ra->rank; rk_n = ra->n; rk_npad = ra->npad; rk_x = ra->x; rk_xT = ra->xT; rk_E = ra->E; rk_wout = ra->w_out;
+    rk_part = v_in.vv[blockIdx.x / G].part;
   }
   using CF = V2Cfg<DMAX>;
   constexpr int TRI = CF::TRI, NB = CF::NB, NE4 = CF::NE4;
@@ -517,9 +524,9 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
   constexpr int tri = d * (d + 1) / 2;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int team = warp >> 2, wq = warp & 3, tt = t & 127;
-  const long n = a.n, np = a.npad;
+  const long n = rk_n, np = rk_npad;
   const long ntiles = np / kV2TS;
-  const bool writer = (a.rank == 0 && bid == 0);
+  const bool writer = (rk_rank == 0 && bid == 0);
   EmCtrl *ctrl = a.ctrl;
 
   // shared memory: [region0: ring, aliased by the end-of-pass reduction scratch][mu][B][rec][tot][part][LeaderS]
@@ -561,8 +568,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
         for (long i = (long)bid * NCONS + t; i < n; i += (long)G * NCONS) {
 #pragma unroll
           for (int j = 0; j < DMAX; j++) {
-            const double xv = a.x[i * d + j];
-            __stcg(a.xT + v2_x_at(i, j, d), xv);
+            const double xv = rk_x[i * d + j];
+            __stcg(rk_xT + v2_x_at(i, j, d), xv);
             acc[j] += xv;
             acc[DMAX + j] = fma(xv, xv, acc[DMAX + j]);
           }
@@ -615,12 +622,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
         if (lane == 0) {
           s_gen[st] = (unsigned)(seq / (unsigned)NS) + 1u;  // fills issued for this stage
           mbar_expect_tx(&s_full[st], (uint32_t)(rows * kV2TS * 8));
-          tma_load_row(xs, a.xT + (size_t)tl * d * kV2TS, (uint32_t)(d * kV2TS * 8), &s_full[st]);
+          tma_load_row(xs, rk_xT + (size_t)tl * d * kV2TS, (uint32_t)(d * kV2TS * 8), &s_full[st]);
         }
         __syncwarp();
         if (lane >= 1 && lane <= nrun) {
           const int l0 = s_run[2 * (lane - 1)], len = s_run[2 * (lane - 1) + 1];
-          tma_load_row(Es + l0 * kV2TS, a.E + ((size_t)tl * Lmax + S.slot[l0]) * kV2TS, (uint32_t)(len * kV2TS * 8), &s_full[st]);
+          tma_load_row(Es + l0 * kV2TS, rk_E + ((size_t)tl * Lmax + S.slot[l0]) * kV2TS, (uint32_t)(len * kV2TS * 8), &s_full[st]);
         }
       };
       // prologue: the ring is idle (end-of-pass barrier): warp 0 fills it.  The density rows it copies were written
@@ -682,12 +689,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
               }
               const double e = exp(fma(-0.5, q, c1));
               Ecol[l * kV2TS] = e;
-              if (valid) __stcg(a.E + v2_e_at(i, S.slot[l], Lmax), e);
+              if (valid) __stcg(rk_E + v2_e_at(i, S.slot[l], Lmax), e);
             }
           } else if (dens) {
             const double enew = exp(fma(-0.5, v2_solve_cols<DMAX>(s_rec, xv), s_rec[3]));
             Ecol[cc * kV2TS] = enew;
-            if (valid) __stcg(a.E + v2_e_at(i, cslot, Lmax), enew);
+            if (valid) __stcg(rk_E + v2_e_at(i, cslot, Lmax), enew);
           }
           // sum_l lam_l E_il in component order (as the reference adds them)
           double sum;
@@ -804,8 +811,8 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
 
     // ------------------------------------------------------------------ exchange: partial rows -> totals everywhere
     const long long tk1 = clock64();
-    V2Sync *me = v.sync[a.rank];
-    for (int q = t; q < nv; q += blockDim.x) __stcg(v.part + (size_t)q * G + bid, s_part[q]);
+    V2Sync *me = v.sync[rk_rank];
+    for (int q = t; q < nv; q += blockDim.x) __stcg(rk_part + (size_t)q * G + bid, s_part[q]);
     __syncthreads();
     if (t == 0) {
       __threadfence();
@@ -828,7 +835,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
 #pragma unroll
           for (int m = 0; m < KB; m++) {
             const int b = lane + 32 * m;
-            vv[k][m] = (q < nv && b < G) ? ld_cg(v.part + (size_t)q * G + b) : 0.0;
+            vv[k][m] = (q < nv && b < G) ? ld_cg(rk_part + (size_t)q * G + b) : 0.0;
           }
         }
 #pragma unroll
@@ -837,7 +844,7 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
           double r = 0.0;
 #pragma unroll
           for (int m = 0; m < KB; m++) r += vv[k][m];
-          for (int b = lane + 32 * KB; b < G; b += 32) r += ld_cg(v.part + (size_t)(q < nv ? q : 0) * G + b);  // larger grids
+          for (int b = lane + 32 * KB; b < G; b += 32) r += ld_cg(rk_part + (size_t)(q < nv ? q : 0) * G + b);  // larger grids
           r = warp_sum(r);
           if (lane == 0 && q < nv) s_tot[q] = r;
         }
@@ -845,12 +852,12 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
       __syncthreads();
       for (int q = t; q < nv * a.ndev; q += blockDim.x) {
         const int g = q / nv, k = q - g * nv;
-        v.sync[g]->inbox[par][a.rank][k] = s_tot[k];
+        v.sync[g]->inbox[par][rk_rank][k] = s_tot[k];
       }
       if (a.ndev > 1) __threadfence_system();
       else __threadfence();
       __syncthreads();
-      if (t < a.ndev) st_release_sys(&v.sync[t]->flag[a.rank][0], epoch + 1u);
+      if (t < a.ndev) st_release_sys(&v.sync[t]->flag[rk_rank][0], epoch + 1u);
     }
     if (t < a.ndev) {  // every CTA: wait until every GPU's row of this epoch is in the local inbox
       const unsigned *f = &me->flag[t][0];
@@ -911,14 +918,14 @@ __global__ void __launch_bounds__(NTEAM * 128, 1) em_fit_v2_kernel(EmArgs a_in, 
     for (int q = t; q < Lw * tri; q += blockDim.x) ctrl->B[q / tri][q % tri] = s_B[q];
   }
   // optional dump of the responsibilities of the working state (step-parity tests)
-  if (a.w_out != nullptr) {
+  if (rk_wout != nullptr) {
     const int L = S.L;
     for (long i = (long)bid * blockDim.x + t; i < n; i += (long)G * blockDim.x) {
       double sum = 0.0;
-      for (int l = 0; l < L; l++) sum += S.lam[l] * __ldcg(a.E + v2_e_at(i, S.slot[l], Lmax));
+      for (int l = 0; l < L; l++) sum += S.lam[l] * __ldcg(rk_E + v2_e_at(i, S.slot[l], Lmax));
       for (int l = 0; l < L; l++) {
-        const double e = __ldcg(a.E + v2_e_at(i, S.slot[l], Lmax));
-        a.w_out[(size_t)i * a.Lmax + l] = (sum > 0) ? S.lam[l] * e / sum : 1.0 / L;
+        const double e = __ldcg(rk_E + v2_e_at(i, S.slot[l], Lmax));
+        rk_wout[(size_t)i * a.Lmax + l] = (sum > 0) ? S.lam[l] * e / sum : 1.0 / L;
       }
     }
   }

@@ -3,7 +3,7 @@
 # Run on the GPU box: gpurun -- 'bash profiles/run_ncu.sh <tag>'.  Outputs land in gpurun_out/.
 # Each profiled command is first run plain (must exit 0), then under ncu.
 set -u
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 2 --warmup 1 --no-cpu --sweeps 50 --em-n 200000 --em-maxit 3 --em-steps 1"
 RJ="python profiles/rj_only.py 1048576 50 toy1"
@@ -17,7 +17,7 @@ $RJ > gpurun_out/plain_rj_$TAG.log 2>&1 || { echo "plain rj failed"; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:rj_sweep_kernel -s 2 -c 1 \
     -o gpurun_out/prof_rj_$TAG -f $RJ > gpurun_out/ncu_rj_$TAG.log 2>&1
 $EM > gpurun_out/plain_em_$TAG.log 2>&1 || { echo "plain em failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:em_fit_kernel -s 1 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:em_fit -s 1 -c 1 \
     -o gpurun_out/prof_em_$TAG -f $EM > gpurun_out/ncu_em_$TAG.log 2>&1
 cat gpurun_out/plain_rj_$TAG.log gpurun_out/plain_em_$TAG.log
 ls -la gpurun_out/ | grep $TAG
