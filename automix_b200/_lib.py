@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libautomix.so")
+LIB_PATH = os.environ.get("AMX_LIB_PATH") or os.path.join(HERE, "lib", "libautomix.so")  # (override: build experiments)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -44,7 +44,7 @@ EXPORTS = [
     "amx_mix_logpdf_dev", "amx_target_gaussmix", "amx_target_quad", "amx_target_coalmine", "amx_target_mixnorm", "amx_target_plugin",
     "amx_target_host_scalar", "amx_target_host_batched", "amx_target_destroy", "amx_target_eval",
     "amx_proposal_create", "amx_proposal_destroy", "amx_rj_create", "amx_rj_destroy",
-    "amx_rj_set_tape", "amx_rj_set_pk_mode", "amx_rj_get_pk_shared", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
+    "amx_rj_set_tape", "amx_rj_set_sort", "amx_rj_set_pk_mode", "amx_rj_get_pk_shared", "amx_rj_set_chain_base", "amx_rj_set_modes", "amx_rwm_set_dof", "amx_copy_dev", "amx_rj_init_chains", "amx_rj_set_state", "amx_rj_get_state", "amx_rj_sweeps",
     "amx_rj_collect", "amx_rj_visit_se", "amx_rj_get_trace", "amx_rj_visits_dev", "amx_sokal", "amx_sokal_dev", "amx_rj_sokal",
     "amx_rj_moments_reset", "amx_rj_moments_accumulate", "amx_rj_moments_get", "amx_em_fit", "amx_em_fit_dev",
     "amx_em_draw_init", "amx_em_fit_multi", "amx_autorj_fit", "amx_rwm_adapt", "amx_rwm_adapt_all", "amx_fam_plan", "amx_fam_pack",
@@ -99,6 +99,7 @@ def lib():
     L.amx_rj_set_tape.argtypes = [C.c_void_p, _dp, C.c_long]
     L.amx_rj_set_chain_base.argtypes = [C.c_void_p, C.c_uint64]
     L.amx_rj_set_pk_mode.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.amx_rj_set_sort.argtypes = [C.c_void_p, C.c_int]
     L.amx_rj_get_pk_shared.argtypes = [C.c_void_p, _dp, _ip, _dp]
     L.amx_rj_set_modes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.amx_rwm_set_dof.argtypes = [C.c_int]
@@ -292,6 +293,10 @@ class RjPopulation:
     def set_pk_mode(self, population: bool, segment_sweeps: int = 0):
         """amx_rj_set_pk_mode: per-chain pk adaptation (the reference's rule) or one pk shared by the population."""
         check(lib().amx_rj_set_pk_mode(self.h, 1 if population else 0, int(segment_sweeps)))
+
+    def set_sort(self, sweeps_per_sort: int = -1):
+        """amx_rj_set_sort: re-sort the chains by (model, proposed model) before every n sweeps (-1 automatic, 0 off)."""
+        check(lib().amx_rj_set_sort(self.h, int(sweeps_per_sort)))
 
     def pk_shared(self):
         pk = np.zeros(self.nm)

@@ -29,6 +29,8 @@ struct amx_rj {
   long gam_cap;
   int pk_mode, pk_seg;      // AMX_PK_PER_CHAIN / AMX_PK_POPULATION; sweeps per population update
   RjPkShared *pk_shared;    // device
+  int sort_seg;             // sorted mode: -1 automatic, 0 off, n > 0 re-sort the chains before every n sweeps
+  RjSort so;                // its device buffers (allocated on first use)
   int *tr_k;
   double *tr_lp, *tr_theta, *tr_pk;
   long tr_cap, last_nsweeps;
@@ -88,6 +90,48 @@ static bool is_host_target(const amx_rj *rj) {
   return rj->tgt->d.kind == kTargetHostScalar || rj->tgt->d.kind == kTargetHostBatched;
 }
 
+// ---- sorted mode (rj_sort_*_kernel, amx_rj_kernels.cuh) ----------------------------------------------------------
+// Sweeps per sort for this call: 0 = unsorted.  Automatic: the wide configurations (a model with more than 8
+// coordinates) on a device plug-in, where a warp of mixed models pays for its widest chain and the fixed-dimension
+// quadratic forms (quad_form_wide) diverge; the small register-resident configurations (d <= 8) run hundreds of
+// sweeps per launch with their state in registers and lose more to the per-sort state traffic than they gain.
+static int sort_segment(const amx_rj *rj) {
+  if (is_host_target(rj) || rj->nm < 2) return 0;
+  if (rj->sort_seg >= 0) return rj->sort_seg;
+  if (const char *e = getenv("AMX_RJ_SORT")) return atoi(e);
+  return rj->dmax > 8 ? 1 : 0;
+}
+static int sort_alloc(amx_rj *rj) {
+  if (rj->so.order) return AMX_OK;
+  RjSort &so = rj->so;
+  const amx_fam_hdr &h = rj->prop->hdr;
+  so.nb = rj->nm * rj->nm;
+  // rank of a model in the order "widest first" (ties by index)
+  for (int k = 0; k < rj->nm; k++) {
+    int r = 0;
+    for (int q = 0; q < rj->nm; q++)
+      if (h.dims[q] > h.dims[k] || (h.dims[q] == h.dims[k] && q < k)) r++;
+    so.rank[k] = (unsigned char)r;
+  }
+  AMX_CUDA(cudaMalloc(&so.keys, sizeof(int) * (size_t)rj->C));
+  AMX_CUDA(cudaMalloc(&so.order, sizeof(int) * (size_t)rj->C));
+  AMX_CUDA(cudaMalloc(&so.hist, sizeof(int) * 3 * kSortBuckets));
+  so.start = so.hist + kSortBuckets;
+  so.cursor = so.start + kSortBuckets;
+  AMX_CUDA(cudaMemsetAsync(so.hist, 0, sizeof(int) * 3 * kSortBuckets, stream()));
+  return AMX_OK;
+}
+static int sort_chains(amx_rj *rj, const RjLaunch &a) {
+  const unsigned grid = (unsigned)((rj->C + kSortThreads - 1) / kSortThreads);
+  if (rj->tape_dev) rj_sort_key_kernel<TapeStream><<<grid, kSortThreads, 0, stream()>>>(a, rj->so);
+  else rj_sort_key_kernel<PhiloxStream><<<grid, kSortThreads, 0, stream()>>>(a, rj->so);
+  rj_sort_scan_kernel<<<1, kSortBuckets, 0, stream()>>>(rj->so);
+  rj_sort_scatter_kernel<<<grid, kSortThreads, 0, stream()>>>(rj->so, rj->C);
+  count_launch(3);
+  AMX_CUDA(cudaGetLastError());
+  return AMX_OK;
+}
+
 static int split_alloc(amx_rj *rj) {
   if (rj->sp.thn) return AMX_OK;
   const size_t C = (size_t)rj->C;
@@ -96,10 +140,10 @@ static int split_alloc(amx_rj *rj) {
   AMX_CUDA(cudaMalloc(&rj->sp.lpn, sizeof(double) * C));
   AMX_CUDA(cudaMalloc(&rj->sp.kn, sizeof(int) * C));
   AMX_CUDA(cudaMalloc(&rj->sp.carry, sizeof(double) * 5 * C));
-  AMX_CUDA(cudaMemset(rj->sp.thn, 0, sizeof(double) * C * rj->dmax));
-  AMX_CUDA(cudaMemset(rj->sp.lpn, 0, sizeof(double) * C));
-  AMX_CUDA(cudaMemset(rj->sp.kn, 0, sizeof(int) * C));
-  AMX_CUDA(cudaMemset(rj->sp.carry, 0, sizeof(double) * 5 * C));
+  AMX_CUDA(cudaMemsetAsync(rj->sp.thn, 0, sizeof(double) * C * rj->dmax, stream()));
+  AMX_CUDA(cudaMemsetAsync(rj->sp.lpn, 0, sizeof(double) * C, stream()));
+  AMX_CUDA(cudaMemsetAsync(rj->sp.kn, 0, sizeof(int) * C, stream()));
+  AMX_CUDA(cudaMemsetAsync(rj->sp.carry, 0, sizeof(double) * 5 * C, stream()));
   AMX_CUDA(cudaMallocHost(&rj->h_thn, sizeof(double) * C * rj->dmax));
   AMX_CUDA(cudaMallocHost(&rj->h_lpn, sizeof(double) * C));
   AMX_CUDA(cudaMallocHost(&rj->h_keval, sizeof(int) * C));
@@ -262,6 +306,7 @@ amx_rj *amx_rj_create(const amx_proposal *p, const amx_target *t, long nchains, 
   rj_pk_reset_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->nm);
   rj->pk_mode = AMX_PK_PER_CHAIN;
   rj->pk_seg = 25;
+  rj->sort_seg = -1;
   AMX_CUDA_PTR(cudaEventCreate(&rj->e0));
   AMX_CUDA_PTR(cudaEventCreate(&rj->e1));
   rj->pending = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
@@ -276,6 +321,7 @@ void amx_rj_destroy(amx_rj *rj) {
   cudaFree(s.nreinit); cudaFree(s.draws); cudaFree(rj->init_dev); cudaFree(rj->tape_dev);
   cudaFree(rj->visits_dev); cudaFree(rj->cnt_dev); cudaFree(rj->status_dev); cudaFree(rj->gam_dev); cudaFree(rj->pk_shared); cudaFree(rj->grp_dev);
   cudaFree(rj->tr_k); cudaFree(rj->tr_lp); cudaFree(rj->tr_theta); cudaFree(rj->tr_pk);
+  cudaFree(rj->so.keys); cudaFree(rj->so.order); cudaFree(rj->so.hist);
   cudaEventDestroy(rj->e0);
   cudaEventDestroy(rj->e1);
   for (auto &pr : *rj->pending) {
@@ -518,20 +564,30 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
   rj_gamma_kernel<<<(unsigned)((nsweeps + 255) / 256), 256, 0, stream()>>>(rj->gam_dev, rj->sweep_i, (int)nsweeps);
   count_launch();
   AMX_CUDA(cudaEventRecord(e0, stream()));
-  // Population pk mode while adapting: segments of pk_seg sweeps, each followed by the shared update.  Otherwise
-  // (per-chain mode, or nothing to adapt) the whole call is one launch.
+  // Population pk mode while adapting: segments of pk_seg sweeps, each followed by the shared update.  Sorted mode:
+  // launches of sort_seg sweeps, each preceded by the sort.  Otherwise the whole call is one launch.
   const long seg = (pop && adapt) ? (long)rj->pk_seg : nsweeps;
+  const long sseg = sort_segment(rj);
   int rc = AMX_OK;
+  if (sseg > 0) {
+    rc = sort_alloc(rj);
+    a.order = rj->so.order;
+  }
   for (long off = 0; off < nsweeps && rc == AMX_OK; off += seg) {
     const long m = (nsweeps - off < seg) ? nsweeps - off : seg;
-    a.gam = rj->gam_dev + off;
-    a.sweep0 = rj->sweep_i + (unsigned long long)off;
-    a.nsweeps = (int)m;
-    a.tr_off = off;
-    if (is_host_target(rj)) rc = use_mailbox() ? mailbox_sweeps(rj, a) : split_sweeps(rj, a);
-    else rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
+    const long step = sseg > 0 ? sseg : m;
+    for (long o2 = 0; o2 < m && rc == AMX_OK; o2 += step) {
+      a.gam = rj->gam_dev + off + o2;
+      a.sweep0 = rj->sweep_i + (unsigned long long)(off + o2);
+      a.nsweeps = (int)((m - o2 < step) ? m - o2 : step);
+      a.tr_off = off + o2;
+      if (sseg > 0) rc = sort_chains(rj, a);
+      if (rc) break;
+      if (is_host_target(rj)) rc = use_mailbox() ? mailbox_sweeps(rj, a) : split_sweeps(rj, a);
+      else rc = rj->tape_dev ? launch_tgt<TapeStream>(rj, a) : launch_tgt<PhiloxStream>(rj, a);
+    }
     if (rc == AMX_OK && pop) {  // also while burning: the histogram baseline must follow the visits
-      rj_pk_population_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->visits_dev, a.gam, (int)m, rj->nm, adapt);
+      rj_pk_population_kernel<<<1, 32, 0, stream()>>>(rj->pk_shared, rj->visits_dev, rj->gam_dev + off, (int)m, rj->nm, adapt);
       count_launch();
     }
   }
@@ -544,6 +600,12 @@ int amx_rj_sweeps(amx_rj *rj, long nsweeps, int burning, int do_adapt) {
   rj->pending->push_back({e0, e1});
   rj->sweep_i += (unsigned long long)nsweeps;
   rj->last_nsweeps = nsweeps;
+  return AMX_OK;
+}
+
+int amx_rj_set_sort(amx_rj *rj, int sweeps_per_sort) {
+  if (!rj || sweeps_per_sort < -1) return fail(AMX_EINVAL, "amx_rj_set_sort: bad arguments");
+  rj->sort_seg = sweeps_per_sort;
   return AMX_OK;
 }
 

@@ -153,11 +153,10 @@ __device__ __forceinline__ void rwm_coord_finish(ChainRegs<CFG> &c, U &u, int j,
 template <class CFG, class PA>
 __device__ __forceinline__ double alloc_weights(const ProposalView &P, int k, const double (&x)[CFG::DMAX], PA &p) {
   const int d = P.h->dims[k], L = P.h->ncomp[k];
-  double r[CFG::DMAX];
   double s = 0.0;
   for (int l = 0; l < L; l++) {
     const double *rec = P.rec(k, l);
-    const double v = exp(rec[1] + (fma(-0.5, solve_lower<CFG::DMAX>(rec, d, x, r), rec[3])));
+    const double v = exp(rec[1] + (fma(-0.5, quad_form<CFG::DMAX>(rec, d, x), rec[3])));
     p.set(l, v);
     s += v;
   }
@@ -407,6 +406,7 @@ struct RjLaunch {
   const double *tape;          // parity mode
   unsigned long long tape_stride;
   const double *pk_shared;     // population pk mode: [nmodels] jump probabilities shared by every chain (else NULL)
+  const int *order;            // sorted mode: slot -> chain, chains grouped by (model, proposed model), widest first (else NULL)
   const double *gam;           // [nsweeps] pk-adaptation step sizes (sweep_i+1)^(-2/3)
   unsigned long long sweep0;   // sweep_i of the first sweep of this launch
   int nsweeps;

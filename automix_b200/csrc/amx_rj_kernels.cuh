@@ -93,14 +93,19 @@ __device__ __forceinline__ void stage_blobs(const RjLaunch &a, double *smem, boo
   }
 }
 
+// dlo: coordinates to load.  A chain in model k never reads its coordinates beyond dims[k] (they are rewritten in full
+// when a jump to a wider model is accepted), so the fused kernel loads dims[k] of them and stores up to the widest
+// model the chain visited during the launch; what lies beyond keeps its old value in memory either way.
 template <class CFG>
-__device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, long id, const double *pk_shared = nullptr) {
+__device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, long id, const double *pk_shared = nullptr,
+                                           int dlo = AMX_MAX_DIM) {
   c.k = s.k[id];
   c.lp = s.lp[id];
   c.pkllim = s.pkllim[id];
   c.nreinit = s.nreinit[id];
+  if (dlo > s.dmax) dlo = s.dmax;
 #pragma unroll
-  for (int i = 0; i < CFG::DMAX; i++) c.th[i] = (i < s.dmax) ? s.theta[(long)i * s.C + id] : 0.0;
+  for (int i = 0; i < CFG::DMAX; i++) c.th[i] = (i < dlo) ? s.theta[(long)i * s.C + id] : 0.0;
 #pragma unroll
   for (int i = 0; i < CFG::DMAX; i++) c.thn[i] = c.th[i];
 #pragma unroll
@@ -112,17 +117,21 @@ __device__ __forceinline__ void load_chain(ChainRegs<CFG> &c, const RjState &s, 
   c.lr_pre = c.t_alloc = c.t_wt = c.t_det = c.gam = 0.0;
 }
 template <class CFG>
-__device__ __forceinline__ void store_chain(const ChainRegs<CFG> &c, const RjState &s, long id) {
+__device__ __forceinline__ void store_chain(const ChainRegs<CFG> &c, const RjState &s, long id, int dhi = AMX_MAX_DIM,
+                                            bool with_pk = true) {
   s.k[id] = c.k;
   s.lp[id] = c.lp;
   s.pkllim[id] = c.pkllim;
   s.nreinit[id] = c.nreinit;
+  if (dhi > s.dmax) dhi = s.dmax;
 #pragma unroll
   for (int i = 0; i < CFG::DMAX; i++)
-    if (i < s.dmax) s.theta[(long)i * s.C + id] = c.th[i];
+    if (i < dhi) s.theta[(long)i * s.C + id] = c.th[i];
+  if (with_pk) {
 #pragma unroll
-  for (int j = 0; j < CFG::NMAX; j++)
-    if (j < s.nmodels) s.pk[(long)j * s.C + id] = c.pk[j];
+    for (int j = 0; j < CFG::NMAX; j++)
+      if (j < s.nmodels) s.pk[(long)j * s.C + id] = c.pk[j];
+  }
 }
 
 template <class RNG>
@@ -146,6 +155,17 @@ __device__ __forceinline__ void open_stream<TapeStream>(TapeStream &u, const RjL
 #ifndef AMX_RJ_MIN_BLOCKS
 #define AMX_RJ_MIN_BLOCKS 4
 #endif
+// Wide configurations (d > 2), measured on B200 with the sorted population (C5-RJ / coal-mining, 2^18 chains,
+// chain-sweeps/s): straight-line sweep with three inlined plug-in evaluations 3.72e8 / 2.77e8, phase loop (one copy)
+// 3.70e8 / 2.92e8 -- instruction fetch is the largest stall of these kernels (ncu: 1.9 / 6.6 "no instruction" stalls
+// per issue), so the smaller loop wins where the plug-in is large.  Register cap for 3 CTAs per SM: 166 registers,
+// no spills (255 uncapped; 128 for 4 CTAs spills and is not faster).
+#ifndef AMX_RJ_PHASE_LOOP_WIDE
+#define AMX_RJ_PHASE_LOOP_WIDE 1
+#endif
+#ifndef AMX_RJ_MIN_BLOCKS_WIDE
+#define AMX_RJ_MIN_BLOCKS_WIDE 3
+#endif
 template <class CFG, class TGT>
 #if AMX_RJ_EVAL_INLINE
 __device__ __forceinline__
@@ -160,7 +180,7 @@ __device__ __noinline__
 // ---- the fused sweep kernel ------------------------------------------------------------------
 enum { kPhaseBlock = 0, kPhaseCoord, kPhaseJump, kPhaseIdle };
 template <class CFG, class TGT, class RNG>
-__global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCKS : 1)) rj_sweep_kernel(RjLaunch a, int staged) {
+__global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCKS : AMX_RJ_MIN_BLOCKS_WIDE)) rj_sweep_kernel(RjLaunch a, int staged) {
   extern __shared__ double smem[];
   __shared__ unsigned s_hist[kRjWarps][CFG::NMAX];
   __shared__ int s_clp[AMX_MAX_MODELS];
@@ -168,12 +188,17 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   __shared__ int s_status;
   // allocation weights of the jump: [component][thread] in shared memory for the register-resident configurations
   __shared__ double s_pa[(CFG::DMAX <= 8) ? CFG::LMAX * kRjThreads : 1];
+  // sorted mode: a CTA's chains come from anywhere in the population, so the per-group visit counts (Monte-Carlo
+  // error, amx_rj_visit_se) are kept per chain id -- group = (id / 128) mod kRjGroups, a fixed partition of the chains
+  __shared__ unsigned s_grp[kRjGroups * CFG::NMAX];
   AllocVec<CFG> pa;
   if constexpr (CFG::DMAX <= 8) pa.p = s_pa + threadIdx.x;
 
   const void *pb, *tb;
   stage_blobs(a, smem, staged != 0, pb, tb);
   for (int i = threadIdx.x; i < kRjWarps * CFG::NMAX; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+  if (a.order)
+    for (int i = threadIdx.x; i < kRjGroups * CFG::NMAX; i += blockDim.x) s_grp[i] = 0;
   if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) s_status = 0;
   __syncthreads();
@@ -195,14 +220,17 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   for (long base = (long)blockIdx.x * blockDim.x; base < a.st.C; base += (long)gridDim.x * blockDim.x) {
   const long gid = base + threadIdx.x;
   const bool active = gid < a.st.C;
-  const long id = active ? gid : a.st.C - 1;  // tail lanes shadow the last chain, never write
+  const long slot = active ? gid : a.st.C - 1;  // tail lanes shadow the last chain, never write
+  const long id = a.order ? (long)a.order[slot] : slot;
 
   ChainRegs<CFG> c;
-  load_chain(c, a.st, id, a.pk_shared);
+  int dhi = P.h->dims[a.st.k[id]];  // widest model this chain visits during the launch
+  load_chain(c, a.st, id, a.pk_shared, dhi);
   RNG u;
   const unsigned long long draws0 = a.st.draws[id];
   open_stream(u, a, id, draws0);
-  const bool traced = active && gid < a.ntrace;
+  const bool traced = active && id < a.ntrace;
+  unsigned *my_grp = s_grp + (int)((id >> 7) % kRjGroups) * CFG::NMAX;
 
   for (int s = 0; s < a.nsweeps; s++) {
     const unsigned long long sweep_i = a.sweep0 + (unsigned long long)s;
@@ -213,7 +241,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
     // over the grid; otherwise coordinate phase j runs on the lanes whose model has more than j coordinates and the
     // jump waits for the widest model in the warp, so the lanes of a warp always take it together.
     const bool blockmove = (sweep_i % 10ull == 0ull);
-    if constexpr (CFG::DMAX <= 8) {
+    if constexpr (CFG::DMAX <= 8 || AMX_RJ_PHASE_LOOP_WIDE) {
       int last = 1;
       if (blockmove) {
         c.flops += (unsigned)(s_clp[c.k] + 3 * d + 10);
@@ -234,8 +262,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
         else if (kind == kPhaseJump) rj_finish(c, P, u, lpn, a.adapt != 0);
       }
     } else {
-      // large configurations (vectors in local memory, one or two CTAs per SM): code size is not what limits them,
-      // and the straight-line form measured 5 % faster
+      // straight-line form (AMX_RJ_PHASE_LOOP_WIDE=0): three inlined copies of the plug-in evaluation
       if (blockmove) {
         rwm_block_propose(c, P, u, md);
         const double lpn = eval_target<CFG, TGT>(T, c.k, c.thn);
@@ -255,6 +282,7 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
       rj_finish(c, P, u, lpn, a.adapt != 0);
     }
     if (c.lp != c.lp) status |= 2;
+    dhi = max(dhi, P.h->dims[c.k]);
 
     // model-visit histogram: one ballot per model, lane 0 adds the population count
     __syncwarp();
@@ -262,8 +290,9 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
       const unsigned b = __ballot_sync(0xffffffffu, active && c.k == m);
       if (lane == 0) s_hist[warp][m] += __popc(b);
     }
+    if (a.order && active) atomicAdd(&my_grp[c.k], 1u);
     if (traced) {
-      const long row = (long)gid * a.tr_stride + a.tr_off + s;
+      const long row = (long)id * a.tr_stride + a.tr_off + s;
       a.tr_k[row] = c.k;
       a.tr_lp[row] = c.lp;
       const int dk = P.h->dims[c.k];
@@ -278,7 +307,8 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   c.try_b = (unsigned)((a.sweep0 + (unsigned long long)a.nsweeps + 9ull) / 10ull - (a.sweep0 + 9ull) / 10ull);
 
   if (active) {
-    store_chain(c, a.st, id);
+    // pk moves only while adapting per chain; the shared pk of the population mode is stored as before
+    store_chain(c, a.st, id, dhi, a.adapt != 0 || a.pk_shared != nullptr);
     a.st.draws[id] = u.n;
   }
   // counters: warp reduce, one shared atomic per warp, one global atomic per CTA
@@ -296,9 +326,109 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
     unsigned long long t = 0;
     for (int w = 0; w < kRjWarps; w++) t += s_hist[w][threadIdx.x];
     atomicAdd(&a.visits[threadIdx.x], t);
-    atomicAdd(&a.visits_grp[(blockIdx.x % kRjGroups) * AMX_MAX_MODELS + threadIdx.x], t);
+    if (!a.order) atomicAdd(&a.visits_grp[(blockIdx.x % kRjGroups) * AMX_MAX_MODELS + threadIdx.x], t);
   }
+  if (a.order)
+    for (int i = threadIdx.x; i < kRjGroups * CFG::NMAX; i += blockDim.x)
+      if (s_grp[i]) atomicAdd(&a.visits_grp[(i / CFG::NMAX) * AMX_MAX_MODELS + (i % CFG::NMAX)], (unsigned long long)s_grp[i]);
   if (threadIdx.x == 0 && s_status) atomicOr(a.status, s_status);
+}
+
+// ---- sorted mode: chains grouped by (model, proposed model) before every launch -------------------------------------
+// One thread per chain means a warp pays for its widest chain: with models of 2 ... 20 coordinates mixed in a warp,
+// every coordinate loop, triangular solve and plug-in evaluation runs at d = 20 for all 32 lanes (C5-RJ: 7.6 times the
+// arithmetic the chains need).  Here the population is counting-sorted before each launch of `sort_seg` sweeps by the
+// pair (current model k, model kn the coming jump will propose), widest first, and the sweep kernel walks the chains in
+// that order, so the lanes of a warp run the same trip counts through the whole sweep.  kn is known in advance: with
+// Gaussian innovations a sweep consumes a fixed number of uniforms before the model draw (3 per coordinate, or
+// 2 ceil(d/2) + 1 for a block move, plus one for the allocation when the mixture has several components), the
+// generators have random access, and pk only changes after the jump -- the same scan of pk as rj_propose (:1138-1169).
+// Per-chain arithmetic and random streams are untouched: results are bit-identical to the unsorted kernel.
+struct RjSort {
+  int *keys;    // [C]
+  int *hist;    // [nb] bucket sizes (zero between sorts)
+  int *start;   // [nb] exclusive prefix
+  int *cursor;  // [nb] (zero between sorts)
+  int *order;   // [C]
+  int nb;
+  unsigned char rank[AMX_MAX_MODELS];  // position of a model in the order "widest first"
+};
+constexpr int kSortThreads = 256;
+constexpr int kSortBuckets = AMX_MAX_MODELS * AMX_MAX_MODELS;
+
+template <class RNG>
+__global__ void __launch_bounds__(kSortThreads) rj_sort_key_kernel(RjLaunch a, RjSort so) {
+  __shared__ int s_h[kSortBuckets];
+  for (int i = threadIdx.x; i < so.nb; i += blockDim.x) s_h[i] = 0;
+  __syncthreads();
+  ProposalView P;
+  P.bind(a.prop_blob);
+  const int nm = P.h->nmodels;
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < a.st.C) {
+    const int k = a.st.k[c];
+    int kn = k;
+    if (nm > 1 && a.modes.dof == 0) {
+      const int d = P.h->dims[k], L = P.h->ncomp[k];
+      const bool blockmove = (a.sweep0 % 10ull == 0ull);
+      const unsigned long long pos =
+          a.st.draws[c] + (unsigned long long)((blockmove ? 2 * ((d + 1) / 2) + 1 : 3 * d) + (L > 1 ? 1 : 0));
+      RNG u;
+      open_stream(u, a, c, 0ull);
+      const double uu = u.at(pos);
+      double t = 0.0;
+      bool found = false;
+      kn = 0;
+      for (int i = 0; i < nm; i++) {
+        t += a.pk_shared ? a.pk_shared[i] : a.st.pk[(long)i * a.st.C + c];
+        if (!found && uu < t) {
+          kn = i;
+          found = true;
+        }
+      }
+    }
+    const int key = (int)so.rank[k] * nm + (int)so.rank[kn];
+    so.keys[c] = key;
+    atomicAdd(&s_h[key], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < so.nb; i += blockDim.x)
+    if (s_h[i]) atomicAdd(&so.hist[i], s_h[i]);
+}
+// exclusive prefix of the bucket sizes (nb <= 1024: one CTA); leaves hist and cursor zero for the next sort
+__global__ void __launch_bounds__(kSortBuckets) rj_sort_scan_kernel(RjSort so) {
+  __shared__ int s[kSortBuckets];
+  const int t = threadIdx.x;
+  const int v = (t < so.nb) ? so.hist[t] : 0;
+  s[t] = v;
+  __syncthreads();
+  for (int o = 1; o < kSortBuckets; o <<= 1) {
+    const int x = (t >= o) ? s[t - o] : 0;
+    __syncthreads();
+    s[t] += x;
+    __syncthreads();
+  }
+  if (t < so.nb) {
+    so.start[t] = s[t] - v;
+    so.hist[t] = 0;
+    so.cursor[t] = 0;
+  }
+}
+__global__ void __launch_bounds__(kSortThreads) rj_sort_scatter_kernel(RjSort so, long C) {
+  __shared__ int s_cnt[kSortBuckets], s_base[kSortBuckets];
+  for (int i = threadIdx.x; i < so.nb; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  const long c = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int key = 0, r = 0;
+  if (c < C) {
+    key = so.keys[c];
+    r = atomicAdd(&s_cnt[key], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < so.nb; i += blockDim.x)
+    if (s_cnt[i]) s_base[i] = so.start[i] + atomicAdd(&so.cursor[i], s_cnt[i]);
+  __syncthreads();
+  if (c < C) so.order[s_base[key] + r] = (int)c;
 }
 
 
@@ -620,6 +750,11 @@ template <class CFG, class TGT, class RNG>
 inline int launch_sweeps(const RjLaunch &a) {
   const size_t need = (size_t)a.prop_bytes + (size_t)a.tgt_bytes;
   int staged = need <= 160 * 1024 ? 1 : 0;
+  // Sorted mode launches once per sweep: copying ~60 KB of blobs into every CTA's shared memory per launch costs more
+  // than it saves (C5-RJ 3.17e8 -> 3.54e8 chain-sweeps/s without), and the lanes of a sorted warp read the same
+  // records, so the L1-cached global loads are broadcasts.
+  if (a.order) staged = 0;
+  if (const char *e = getenv("AMX_RJ_STAGE")) staged = staged && atoi(e);
   const size_t smem = staged ? need : 0;
   auto kern = rj_sweep_kernel<CFG, TGT, RNG>;
   if (smem > 48 * 1024) AMX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -632,7 +767,7 @@ inline int launch_sweeps(const RjLaunch &a) {
     AMX_CUDA(cudaGetDevice(&dev));
     AMX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const char *e = getenv("AMX_RJ_BLOCKS_PER_SM");
-    const unsigned per_sm = e ? (unsigned)atoi(e) : (CFG::DMAX <= 20 ? 2u : 1u);
+    const unsigned per_sm = e ? (unsigned)atoi(e) : (a.order ? 3u : (CFG::DMAX <= 20 ? 2u : 1u));
     const unsigned cap = (unsigned)sms * (per_sm ? per_sm : 1u);
     if (grid > cap) grid = cap;
     // shared memory per SM: per resident CTA the staged blobs, the static arrays (allocation weights, histograms)

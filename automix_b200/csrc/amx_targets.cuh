@@ -48,6 +48,60 @@ __device__ __forceinline__ double solve_lower(const double *rec, int d, const do
   return q;
 }
 
+// ---- |T^-1 (x - mu)|^2 with the dimension as a compile-time constant ----------------------------------------------
+// In the wide configurations (d > 8) x and r are run-time indexed local-memory vectors and the row loop above costs
+// ~13 instructions per multiply-add (ncu, C5-RJ: generic 64-bit address arithmetic for T, LDL/STL of r, the remainder
+// ladders of a partially unrolled loop with trip counts of a few).  With d fixed, r lives in registers, every load has
+// an immediate offset and the body is one load + one DFMA per term -- operation for operation the same arithmetic in
+// the same order, so the value is bit-identical.  One out-of-line copy per translation unit, selected by a switch on d:
+// after the sort (rj_sort_*_kernel) the lanes of a warp share d, so the switch does not diverge.
+constexpr int kQuadFixedMax = 20;
+template <int D>
+__device__ __forceinline__ double quad_fixed(const double *__restrict__ rec, const double *__restrict__ x) {
+  const double *mu = rec + AMX_REC_HEAD, *rd = mu + D, *T = rd + D;
+  double r[D];
+  double q = 0.0;
+#pragma unroll
+  for (int i = 0; i < D; i++) {
+    double v = x[i] - mu[i];
+#pragma unroll
+    for (int j = 0; j < i; j++) v = fma(-T[AMX_TRI(i, j)], r[j], v);
+    r[i] = v * rd[i];
+    q = fma(r[i], r[i], q);
+  }
+  return q;
+}
+static __device__ __noinline__ double quad_form_wide(const double *rec, int d, const double *x) {
+  switch (d) {
+#define AMX_QF(D) case D: return quad_fixed<D>(rec, x);
+    AMX_QF(1) AMX_QF(2) AMX_QF(3) AMX_QF(4) AMX_QF(5) AMX_QF(6) AMX_QF(7) AMX_QF(8) AMX_QF(9) AMX_QF(10)
+    AMX_QF(11) AMX_QF(12) AMX_QF(13) AMX_QF(14) AMX_QF(15) AMX_QF(16) AMX_QF(17) AMX_QF(18) AMX_QF(19) AMX_QF(20)
+#undef AMX_QF
+  }
+  // wider than the unrolled forms: the row loop
+  const double *mu = rec + AMX_REC_HEAD, *rd = mu + d, *T = rd + d;
+  double r[AMX_MAX_DIM];
+  double q = 0.0;
+  for (int i = 0; i < d; i++) {
+    double v = x[i] - mu[i];
+    const double *Ti = T + AMX_TRI(i, 0);
+    for (int j = 0; j < i; j++) v = fma(-Ti[j], r[j], v);
+    r[i] = v * rd[i];
+    q = fma(r[i], r[i], q);
+  }
+  return q;
+}
+// the quadratic form alone (callers that do not need r)
+template <int DMAX>
+__device__ __forceinline__ double quad_form(const double *rec, int d, const double (&x)[DMAX]) {
+  if constexpr (DMAX <= kRegArrayMax) {
+    double r[DMAX];
+    return solve_lower<DMAX>(rec, d, x, r);
+  } else {
+    return quad_form_wide(rec, d, &x[0]);
+  }
+}
+
 // ---- Gaussian-mixture family (toy1, toy2, the synthetic scaling targets) -------------
 struct GaussMixTarget {
   const amx_fam_hdr *h;
@@ -67,16 +121,15 @@ struct GaussMixTarget {
     const int d = h->dims[k], G = h->ncomp[k], st = h->stride[k];
     const double *rec = D + h->off[k];
     const double modw = D[h->ext[k]];
-    double r[DMAX];
     if (flags == AMX_GM_PLAIN) {  // log(modw * sum_g c_g exp(-q_g/2)), as usertoy1.c:72-100
       double s = 0.0;
-      for (int g = 0; g < G; g++) s = fma(rec[g * st + 2], exp(-0.5 * solve_lower<DMAX>(rec + g * st, d, x, r)), s);
+      for (int g = 0; g < G; g++) s = fma(rec[g * st + 2], exp(-0.5 * quad_form<DMAX>(rec + g * st, d, x)), s);
       return log(modw * s);
     }
     // log-sum-exp form: running maximum, rescale on the fly
     double m = -DBL_MAX, s = 0.0;
     for (int g = 0; g < G; g++) {
-      const double a = rec[g * st + 3] - 0.5 * solve_lower<DMAX>(rec + g * st, d, x, r);
+      const double a = rec[g * st + 3] - 0.5 * quad_form<DMAX>(rec + g * st, d, x);
       if (a > m) {
         s = s * exp(m - a) + 1.0;
         m = a;
@@ -287,7 +340,7 @@ struct TargetIsWide<MixNormTarget> {
 // table (amx_target_plugin, include/amx.h).
 struct RjLaunch;
 struct RwmArgs;
-constexpr int kPluginAbi = 2;
+constexpr int kPluginAbi = 3;
 struct PluginVtbl {
   int abi;
   int (*rj_sweeps)(const RjLaunch *a, int dmax, int Lmax, int nm, int tape);

@@ -83,6 +83,24 @@ def _fitted_proposal(amx, wl):
                 mean=np.concatenate(mean), tri=np.concatenate(tri), sig=np.concatenate(sig))
 
 
+def _handmade_proposal(name, dims, init):
+    """A simple hand-made proposal: two components per model around the start point."""
+    wt, mean, tri, sig, ncomp = [], [], [], [], []
+    off = 0
+    for d in dims:
+        x0 = init[off:off + d]
+        off += d
+        sc = np.maximum(np.abs(x0) * 0.15, 0.05) if name == "coalmine" else (np.full(d, 0.25) if name == "c4_mixnorm" else np.ones(d))
+        L = 2
+        ncomp.append(L)
+        wt.append([0.6, 0.4])
+        mean.append(np.concatenate([x0, x0 + 0.5 * sc]))
+        tri.append(np.concatenate([np.diag(sc)[np.tril_indices(d)], np.diag(1.5 * sc)[np.tril_indices(d)]]))
+        sig.append(0.5 * sc)
+    return dict(dims=np.asarray(dims).astype(np.int32), ncomp=np.array(ncomp, np.int32), wt=np.concatenate(wt),
+                mean=np.concatenate(mean), tri=np.concatenate(tri), sig=np.concatenate(sig))
+
+
 @pytest.mark.parametrize("name,nchains,nsweeps", [("toy1", 64, 300), ("toy2", 48, 200), ("c5_rj", 40, 120), ("c1_normal", 33, 250), ("coalmine", 24, 150),
                                                   ("coalmine_fitted", 24, 160), ("c4_mixnorm", 20, 80)])
 def test_population_against_oracle(amx, orc, ht, name, nchains, nsweeps):
@@ -101,21 +119,8 @@ def test_population_against_oracle(amx, orc, ht, name, nchains, nsweeps):
         from automix_b200 import workloads as W
 
         mix = W.ideal_proposal(wl)
-    else:  # a simple hand-made proposal: two components per model around the start point
-        wt, mean, tri, sig, ncomp = [], [], [], [], []
-        off = 0
-        for d in dims:
-            x0 = init[off:off + d]
-            off += d
-            sc = np.maximum(np.abs(x0) * 0.15, 0.05) if name == "coalmine" else (np.full(d, 0.25) if name == "c4_mixnorm" else np.ones(d))
-            L = 2
-            ncomp.append(L)
-            wt.append([0.6, 0.4])
-            mean.append(np.concatenate([x0, x0 + 0.5 * sc]))
-            tri.append(np.concatenate([np.diag(sc)[np.tril_indices(d)], np.diag(1.5 * sc)[np.tril_indices(d)]]))
-            sig.append(0.5 * sc)
-        mix = dict(dims=dims.astype(np.int32), ncomp=np.array(ncomp, np.int32), wt=np.concatenate(wt),
-                   mean=np.concatenate(mean), tri=np.concatenate(tri), sig=np.concatenate(sig))
+    else:
+        mix = _handmade_proposal(name, dims, init)
     tlen = cases.rj_tape_len(dmax, nsweeps) + 8
     tapes = np.stack([cases.tape(1000 + c, tlen) for c in range(nchains)])
     T, P = amx.Target(spec), amx.Proposal(mix)
@@ -352,3 +357,74 @@ def test_deferred_sync_state_transfers(amx):
         want = chk.get_state()
         for key in ("theta", "pk", "lp", "k"):
             assert np.array_equal(pin[key], want[key]), key
+
+
+@pytest.mark.parametrize("name,nchains,pop_pk", [("c5_rj", 3000, False), ("c5_rj", 2500, True), ("toy2", 2000, False),
+                                                 ("coalmine", 1500, False), ("c4_mixnorm", 600, False)])
+def test_sorted_mode_is_bit_identical(amx, name, nchains, pop_pk):
+    """amx_rj_set_sort: chains regrouped by (model, proposed model) before every launch.  Nothing per chain may change:
+    states, traces, counters, uniforms consumed and visit counts equal the unsorted kernel's bit for bit, whatever
+    the number of sweeps per sort; the per-group visit counts (Monte-Carlo error) still partition the total."""
+    from automix_b200 import workloads as W
+
+    wl = cases.workload(name)
+    if wl["target"]["kind"] == "gaussmix":
+        mix = W.ideal_proposal(wl)
+    elif name == "coalmine":
+        mix = _fitted_proposal(amx, wl)
+    else:
+        mix = _handmade_proposal(name, np.asarray(wl["dims"]), cases.default_init(wl, 5))
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    nsw = 47 if name != "c4_mixnorm" else 23
+    init = cases.default_init(wl, 5)
+    out = []
+    for sort in (0, 1, 5):
+        pop = amx.RjPopulation(P, T, nchains, init, seed=31, n_trace=5)
+        pop.set_sort(sort)
+        if pop_pk:
+            pop.set_pk_mode(True, 7)
+        pop.init_chains()
+        pop.sweeps(13, burning=True)
+        pop.sweeps(nsw)  # crosses block-move sweeps (every 10th) at different offsets inside a segment
+        vis, st = pop.collect()
+        p, se, ng = pop.visit_se()
+        s = pop.get_state()
+        tr = pop.trace()
+        out.append((vis, st, s, tr, p, se, ng))
+    v0, st0, s0, tr0 = out[0][:4]
+    assert v0.sum() == nchains * (13 + nsw)
+    for vis, st, s, tr, p, se, ng in out[1:]:
+        assert np.array_equal(vis, v0)
+        for f in ("acc_block", "try_block", "acc_single", "try_single", "acc_jump", "try_jump", "flops", "draws"):
+            assert st[f] == st0[f], f
+        for f in ("theta", "pk", "lp", "k", "nreinit", "pkllim"):
+            assert np.array_equal(s[f], s0[f]), f
+        for f in ("k", "lp", "theta", "pk"):
+            assert np.array_equal(tr[f], tr0[f]), ("trace", f)
+        assert np.allclose(p, v0 / v0.sum(), atol=1e-15) and ng >= 1 and np.all(np.isfinite(se) | (ng < 2))
+
+
+def test_sorted_mode_on_tapes_against_oracle(amx, orc, ht):
+    """The sort reads a chain's coming model draw by random access into its stream; on injected tapes that is a read
+    ahead on the tape.  Sorted chains must still follow the oracle's model sequence exactly."""
+    from automix_b200 import workloads as W
+
+    wl = cases.workload("c5_rj")
+    mix = W.ideal_proposal(wl)
+    nch, nsw = 24, 60
+    dmax = int(max(wl["dims"]))
+    tapes = np.stack([cases.tape(900 + c, cases.rj_tape_len(dmax, nsw) + 8) for c in range(nch)])
+    T, P = amx.Target(wl["target"]), amx.Proposal(mix)
+    pop = amx.RjPopulation(P, T, nch, wl["init"], n_trace=nch)
+    pop.set_sort(1)
+    pop.set_tape(tapes)
+    pop.init_chains()
+    pop.sweeps(nsw)
+    pop.collect()
+    tr = pop.trace()
+    ptr = ht.select(wl["target"])
+    for c in range(nch):
+        orc.tape(tapes[c])
+        r = orc.rj_sweeps(mix, ptr, orc.chain_init(wl["dims"], wl["init"], ptr), nsw)
+        assert np.array_equal(tr["k"][c], r["k"]), c
+        _close(tr["lp"][c], r["lp"], "lp", DRIFT_RTOL)
