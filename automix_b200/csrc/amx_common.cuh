@@ -216,6 +216,51 @@ __device__ __forceinline__ void gauss_pair(U &u, double &z0, double &z1) {
   z1 = z.y;
 }
 
+// ---- out-of-line forms for the wide sweep kernels -------------------------------------------------------------------
+// The wide K3 configurations are bound by instruction fetch (ncu: "no instruction" is their largest stall; ~20 000 SASS
+// instructions with a Philox block inlined at every draw and a Box-Muller at every normal).  There one copy of each,
+// reached by a call, is the better trade; in the small configuration the inlined forms measured faster (above).
+// Values in, values out: no address of the stream escapes, so its state stays in registers.
+#ifndef AMX_RJ_WIDE_OUTLINE
+#define AMX_RJ_WIDE_OUTLINE 1
+#endif
+static __device__ __noinline__ uint4 philox_block_ol(uint32_t b0, uint32_t b1, uint32_t id0, uint32_t id1, uint32_t k0,
+                                                      uint32_t k1) {
+  uint32_t c[4] = {b0, b1, id0, id1};
+  philox4x32_10(c, k0, k1);
+  return make_uint4(c[0], c[1], c[2], c[3]);
+}
+static __device__ __noinline__ double box_muller_sin_ol(double a, double b) { return box_muller_sin(a, b); }
+static __device__ __noinline__ double2 box_muller_pair_ol(double a, double b) { return box_muller_pair(a, b); }
+struct PhiloxStreamOL : PhiloxStream {
+  __device__ __forceinline__ double next() {
+    uint32_t w;
+    if ((n & 3ull) == 0) {
+      const uint4 c = philox_block_ol((uint32_t)(n >> 2), (uint32_t)(n >> 34), id0, id1, k0, k1);
+      w = c.x;
+      w1 = c.y;
+      w2 = c.z;
+      w3 = c.w;
+    } else {
+      w = w1;
+      w1 = w2;
+      w2 = w3;
+    }
+    n++;
+    return u32_to_unit(w);
+  }
+};
+__device__ __forceinline__ double gauss_single(PhiloxStreamOL &u) {
+  const double a = u.next(), b = u.next();
+  return box_muller_sin_ol(a, b);
+}
+__device__ __forceinline__ void gauss_pair(PhiloxStreamOL &u, double &z0, double &z1) {
+  const double a = u.next(), b = u.next();
+  const double2 z = box_muller_pair_ol(a, b);
+  z0 = z.x;
+  z1 = z.y;
+}
+
 // ---- Student-t proposals and random permutation (optional modes of the sampler) -----------------------
 // Gamma(s,1) by rejection, three regimes, exactly the draw order of rgamma() (automix.c:1585-1637).
 template <class U>

@@ -142,6 +142,22 @@ __device__ __forceinline__ void open_stream<PhiloxStream>(PhiloxStream &u, const
   u.open(a.seed, a.chain_base + (unsigned long long)id, consumed);
 }
 template <>
+__device__ __forceinline__ void open_stream<PhiloxStreamOL>(PhiloxStreamOL &u, const RjLaunch &a, long id,
+                                                            unsigned long long consumed) {
+  u.open(a.seed, a.chain_base + (unsigned long long)id, consumed);
+}
+// the generator type the wide configurations run (same stream, out-of-line block and Box-Muller)
+template <class RNG>
+struct WideRng {
+  using type = RNG;
+};
+#if AMX_RJ_WIDE_OUTLINE
+template <>
+struct WideRng<PhiloxStream> {
+  using type = PhiloxStreamOL;
+};
+#endif
+template <>
 __device__ __forceinline__ void open_stream<TapeStream>(TapeStream &u, const RjLaunch &a, long id,
                                                         unsigned long long consumed) {
   u.open(a.tape, a.tape_stride, (unsigned long long)id, consumed);
@@ -786,15 +802,16 @@ inline int launch_sweeps(const RjLaunch &a) {
 
 template <class TGT, class RNG>
 inline int launch_cfg(const RjLaunch &a, int dmax, int Lmax, int nm) {
+  using WRNG = typename WideRng<RNG>::type;
   if constexpr (TargetIsWide<TGT>::value) {
-    if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
-    return launch_sweeps<RjCfgG, TGT, RNG>(a);
+    if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, WRNG>(a);
+    return launch_sweeps<RjCfgG, TGT, WRNG>(a);
   } else {
     const bool plain = a.modes.dof == 0 && a.modes.do_perm == 0;
     if (plain && dmax <= RjCfgS::DMAX && Lmax <= RjCfgS::LMAX && nm <= RjCfgS::NMAX) return launch_sweeps<RjCfgS, TGT, RNG>(a);
     if (dmax <= RjCfgM::DMAX && Lmax <= RjCfgM::LMAX && nm <= RjCfgM::NMAX) return launch_sweeps<RjCfgM, TGT, RNG>(a);
-    if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, RNG>(a);
-    return launch_sweeps<RjCfgG, TGT, RNG>(a);
+    if (dmax <= RjCfgL::DMAX && Lmax <= RjCfgL::LMAX && nm <= RjCfgL::NMAX) return launch_sweeps<RjCfgL, TGT, WRNG>(a);
+    return launch_sweeps<RjCfgG, TGT, WRNG>(a);
   }
 }
 
