@@ -91,15 +91,17 @@ static bool is_host_target(const amx_rj *rj) {
 }
 
 // ---- sorted mode (rj_sort_*_kernel, amx_rj_kernels.cuh) ----------------------------------------------------------
-// Sweeps per sort for this call: 0 = unsorted.  Automatic: the wide configurations (a model with more than 8
-// coordinates) on a device plug-in, where a warp of mixed models pays for its widest chain and the fixed-dimension
-// quadratic forms (quad_form_wide) diverge; the small register-resident configurations (d <= 8) run hundreds of
-// sweeps per launch with their state in registers and lose more to the per-sort state traffic than they gain.
+// Sweeps per sort for this call: 0 = unsorted.  Automatic: populations of >= 65536 chains in the wide configurations
+// (a model with more than 8 coordinates) on a device plug-in, where a warp of mixed models pays for its widest chain.
+// A sorted sweep costs a fixed ~0.1-0.3 ms (three sort kernels, a launch with cold caches, the latency of the widest
+// tile): smaller populations -- the drop-in's default 16384 chains: 0.16 ms per sweep unsorted, 0.42 sorted -- stay on
+// one launch for all sweeps.  The small register-resident configurations (d <= 8) run hundreds of sweeps per launch
+// with their state in registers and lose more to the per-sort state traffic than they gain.
 static int sort_segment(const amx_rj *rj) {
   if (is_host_target(rj) || rj->nm < 2) return 0;
   if (rj->sort_seg >= 0) return rj->sort_seg;
   if (const char *e = getenv("AMX_RJ_SORT")) return atoi(e);
-  return rj->dmax > 8 ? 1 : 0;
+  return (rj->dmax > 8 && rj->C >= 65536) ? 1 : 0;
 }
 static int sort_alloc(amx_rj *rj) {
   if (rj->so.order) return AMX_OK;

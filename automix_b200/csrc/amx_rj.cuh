@@ -62,9 +62,11 @@ struct RjModes {
 struct ProposalView {
   const amx_fam_hdr *h;
   const double *D;
-  __device__ __forceinline__ void bind(const void *blob) {
+  bool uniform_dims;  // the lanes of a warp share (k, kn): fixed-dimension quadratic forms (quad_form)
+  __device__ __forceinline__ void bind(const void *blob, bool uniform = false) {
     h = reinterpret_cast<const amx_fam_hdr *>(blob);
     D = reinterpret_cast<const double *>(h + 1);
+    uniform_dims = uniform;
   }
   __device__ __forceinline__ const double *rec(int k, int l) const { return D + h->off[k] + l * h->stride[k]; }
   __device__ __forceinline__ const double *sig(int k) const { return D + h->ext[k]; }
@@ -156,7 +158,7 @@ __device__ __forceinline__ double alloc_weights(const ProposalView &P, int k, co
   double s = 0.0;
   for (int l = 0; l < L; l++) {
     const double *rec = P.rec(k, l);
-    const double v = exp(rec[1] + (fma(-0.5, quad_form<CFG::DMAX>(rec, d, x), rec[3])));
+    const double v = exp(rec[1] + (fma(-0.5, quad_form<CFG::DMAX>(rec, d, x, P.uniform_dims), rec[3])));
     p.set(l, v);
     s += v;
   }

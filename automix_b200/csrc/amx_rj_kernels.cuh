@@ -219,9 +219,10 @@ __global__ void __launch_bounds__(kRjThreads, (CFG::DMAX <= 2 ? AMX_RJ_MIN_BLOCK
   if (threadIdx.x == 0) s_status = 0;
   __syncthreads();
   ProposalView P;
-  P.bind(pb);
+  P.bind(pb, a.order != nullptr);
   TGT T;
-  T.bind(tb, a.tgt_flags);
+  if constexpr (std::is_same<TGT, GaussMixTarget>::value) T.bind(tb, a.tgt_flags | (a.order ? kTargetFlagUniformDims : 0));
+  else T.bind(tb, a.tgt_flags);
   const int nm = P.h->nmodels;
   if (threadIdx.x < nm) s_clp[threadIdx.x] = T.flops(threadIdx.x);
   __syncthreads();

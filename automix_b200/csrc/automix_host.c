@@ -307,12 +307,26 @@ void estimate_conditional_probs(amSampler *am, int nsweep2) {
   condProbStats *cp = &am->cpstats;
   const int nm = jd->nmodels;
   if (unsupported_modes(am, e, "estimate_conditional_probs")) return;
+  if (nsweep2 < 1) nsweep2 = 1; /* the reference runs max(nsweep2, 10000 d) sweeps whatever the sign (:584) */
   const amx_target *tgt = target_of(am, e);
   if (!tgt) {
     report(e, "plug-in creation", AMX_EINVAL);
     return;
   }
-  if (!cp->isInitialized || cp->nfitmix == NULL) { /* same shapes as the reference's initCondProbStats (:254-299) */
+  /* Rows of the stage-1 traces (sigma and acceptance every 100 sweeps, :648-655).  The reference sizes each model's
+   * arrays by that model's own sweep count but keeps ONE length, the last model's (initCondProbStats :254-299,
+   * rwm_summary_len :266): its report writer then walks every model with that length (logwrite.c:151-154) and reads
+   * past the shorter arrays -- `amcpt` segfaults on the reference.  Here every model gets the longest length, zero
+   * beyond its own rows, and the arrays grow if a later call asks for more sweeps. */
+  int rows_max = 1;
+  for (int k = 0; k < nm; k++) {
+    const int d = jd->model_dims[k];
+    const int nsw = nsweep2 > 10000 * d ? nsweep2 : 10000 * d;
+    const int rows = (nsw + nsw / 10) / 100 > 1 ? (nsw + nsw / 10) / 100 : 1;
+    if (rows > rows_max) rows_max = rows;
+  }
+  const int fresh = !cp->isInitialized || cp->nfitmix == NULL;
+  if (fresh) {
     cp->sig_k_rwm_summary = (double ***)calloc(nm, sizeof(double **));
     cp->nacc_ntry_rwm = (double ***)calloc(nm, sizeof(double **));
     cp->nfitmix = (int *)calloc(nm, sizeof(int));
@@ -321,24 +335,32 @@ void estimate_conditional_probs(amSampler *am, int nsweep2) {
     cp->fitmix_lpn = (double **)calloc(nm, sizeof(double *));
     cp->fitmix_Lkk = (int **)calloc(nm, sizeof(int *));
     for (int k = 0; k < nm; k++) {
-      const int d = jd->model_dims[k];
-      const int nsw = nsweep2 > 10000 * d ? nsweep2 : 10000 * d;
-      const int rows = (nsw + nsw / 10) / 100 > 1 ? (nsw + nsw / 10) / 100 : 1;
-      cp->rwm_summary_len = rows;
-      cp->sig_k_rwm_summary[k] = (double **)malloc(sizeof(double *) * rows);
-      cp->nacc_ntry_rwm[k] = (double **)malloc(sizeof(double *) * rows);
-      cp->sig_k_rwm_summary[k][0] = (double *)calloc((size_t)rows * d, sizeof(double));
-      cp->nacc_ntry_rwm[k][0] = (double *)calloc((size_t)rows * d, sizeof(double));
-      for (int r = 1; r < rows; r++) {
-        cp->sig_k_rwm_summary[k][r] = cp->sig_k_rwm_summary[k][r - 1] + d;
-        cp->nacc_ntry_rwm[k][r] = cp->nacc_ntry_rwm[k][r - 1] + d;
-      }
       const int cap = am->NUM_FITMIX_MAX + 1;
       cp->fitmix_annulations[k] = (int *)calloc(cap, sizeof(int));
       cp->fitmix_costfnnew[k] = (double *)calloc(cap, sizeof(double));
       cp->fitmix_lpn[k] = (double *)calloc(cap, sizeof(double));
       cp->fitmix_Lkk[k] = (int *)calloc(cap, sizeof(int));
     }
+  }
+  if (fresh || rows_max > cp->rwm_summary_len) {
+    for (int k = 0; k < nm; k++) {
+      const int d = jd->model_dims[k];
+      if (cp->sig_k_rwm_summary[k]) {
+        free(cp->sig_k_rwm_summary[k][0]);
+        free(cp->sig_k_rwm_summary[k]);
+        free(cp->nacc_ntry_rwm[k][0]);
+        free(cp->nacc_ntry_rwm[k]);
+      }
+      cp->sig_k_rwm_summary[k] = (double **)malloc(sizeof(double *) * rows_max);
+      cp->nacc_ntry_rwm[k] = (double **)malloc(sizeof(double *) * rows_max);
+      cp->sig_k_rwm_summary[k][0] = (double *)calloc((size_t)rows_max * d, sizeof(double));
+      cp->nacc_ntry_rwm[k][0] = (double *)calloc((size_t)rows_max * d, sizeof(double));
+      for (int r = 1; r < rows_max; r++) {
+        cp->sig_k_rwm_summary[k][r] = cp->sig_k_rwm_summary[k][r - 1] + d;
+        cp->nacc_ntry_rwm[k][r] = cp->nacc_ntry_rwm[k][r - 1] + d;
+      }
+    }
+    cp->rwm_summary_len = rows_max;
     cp->isInitialized = true;
   }
   const long P = e->rwm_chains > 0 ? e->rwm_chains : env_long("AMX_RWM_CHAINS", 1);
@@ -769,6 +791,10 @@ int amx_sampler_load_proposal(amSampler *am, const char *path) {
       for (int i = 0; i < d && rc == AMX_OK; i++)
         for (int j = 0; j <= i && rc == AMX_OK; j++)
           if (fscanf(f, "%lf", &jd->B[k][l][i][j]) != 1) rc = AMX_EINVAL;
+      /* weights and Cholesky diagonals feed logarithms (amx_fam_pack): refuse what would turn into NaN later */
+      if (rc == AMX_OK && !(jd->lambda[k][l] > 0.0)) rc = AMX_EINVAL;
+      for (int i = 0; rc == AMX_OK && i < d; i++)
+        if (!(jd->B[k][l][i][i] > 0.0)) rc = AMX_EINVAL;
       sum += jd->lambda[k][l];
     }
     if (rc == AMX_OK && fabs(sum - 1.0) > 1E-5) rc = AMX_EINVAL;

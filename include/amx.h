@@ -186,7 +186,7 @@ int amx_rj_set_pk_mode(amx_rj *rj, int mode, int segment_sweeps);
  * different dimension the population is counting-sorted on the device before every `sweeps_per_sort` sweeps by
  * (current model, model the coming jump proposes), widest first, so that the lanes of a warp run the same trip counts.
  * Per-chain arithmetic and random streams are untouched (results are bit-identical).  -1 = automatic (default: on with
- * one sweep per sort when the widest model has more than 8 coordinates), 0 = off. */
+ * one sweep per sort for populations of >= 65536 chains whose widest model has more than 8 coordinates), 0 = off. */
 int amx_rj_set_sort(amx_rj *rj, int sweeps_per_sort);
 /* The shared pk of the population mode (pk[nmodels]) and its re-initialisation state; any may be NULL. */
 int amx_rj_get_pk_shared(const amx_rj *rj, double *pk, int *nreinit, double *pkllim);

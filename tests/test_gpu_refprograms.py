@@ -52,3 +52,70 @@ def test_reference_tutorial_on_the_dropin():
     r0, wall0 = _run("ref_tutorial", 600)
     print(f"tutorial.c: drop-in {wall:.1f} s, reference on this host {wall0:.1f} s; p = {p}")
     assert wall < 1.25 * wall0 + 15.0, (wall, wall0)
+
+
+def _am_cli(name, tmp_path, args, timeout=900):
+    exe = os.path.join(REF, name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference at build time; `make -C oracle ref`)")
+    stem = str(tmp_path / name)
+    t0 = time.perf_counter()
+    r = subprocess.run([exe] + args + ["-f", stem], capture_output=True, text=True, timeout=timeout)
+    return r, stem, time.perf_counter() - t0
+
+
+def _report_probs(stem):
+    log = open(stem + "_log.data").read()
+    return [float(x) for x in re.findall(r"^Model \d+: ([0-9.]+)", log.split("Posterior Model Probabilities:")[1], re.M)]
+
+
+@pytest.mark.parametrize("ex,truth,tol", [("toy1", [0.3, 0.7], 0.02), ("toy2", None, None)])
+def test_legacy_cli_and_report_files_on_the_dropin(tmp_path, ex, truth, tol):
+    """the reference's `am*` driver (main.c) and report writer (logwrite.c) compiled UNCHANGED on top
+    of the drop-in library.  The writer walks every legacy array of amSampler -- the stage-1 traces (rwm_summary_len
+    rows per model), the EM traces, and the per-sweep k / lp / pk / theta summaries -- so a complete set of well-formed
+    report files is the widest check of the struct contract; the posterior in <stem>_log.data must agree with the same
+    program on the reference's own library (and with the known 0.3 / 0.7 for toy1)."""
+    n3 = 100000
+    r, stem, wall = _am_cli(f"dropin_am{ex}", tmp_path, ["-n", "100000", "-N", str(n3), "-s", "5"])
+    print(r.stdout[-400:], r.stderr[-400:])
+    assert r.returncode == 0
+    nm = 2 if ex == "toy1" else 5
+    files = ["log", "pk", "k", "lp", "cf", "adapt", "mix", "ac"] + [f"theta{k + 1}" for k in range(nm)]
+    for f in files:
+        assert os.path.getsize(f"{stem}_{f}.data") > 0, f
+    k = [int(x) for x in open(stem + "_k.data").read().split()]
+    assert len(k) == n3 and min(k) >= 1 and max(k) <= nm          # 1-based model index per sweep
+    lp = [ln.split() for ln in open(stem + "_lp.data").read().strip().split("\n")]
+    assert len(lp) == n3 and all(len(x) == 2 for x in lp[:100])
+    pk = [ln.split() for ln in open(stem + "_pk.data").read().strip().split("\n")]
+    assert len(pk) == n3 and len(pk[0]) == nm and abs(sum(float(x) for x in pk[-1]) - 1.0) < 1e-4
+    nth = sum(len(open(f"{stem}_theta{q + 1}.data").read().strip().split("\n")) for q in range(nm))
+    assert nth == n3                                               # every sweep's theta lands in its model's file
+    p = _report_probs(stem)
+    assert len(p) == nm and abs(sum(p) - 1.0) < 1e-4
+    freq = [k.count(q + 1) / n3 for q in range(nm)]
+    assert max(abs(a - b) for a, b in zip(p, freq)) < 1e-5         # the log's posterior is the k file's histogram
+    r0, stem0, wall0 = _am_cli(f"ref_am{ex}", tmp_path, ["-n", "100000", "-N", str(n3), "-s", "5"])
+    assert r0.returncode == 0
+    p0 = _report_probs(stem0)
+    print(f"am{ex}: drop-in {wall:.1f} s p = {p}; reference on this host {wall0:.1f} s p = {p0}")
+    # one chain of 1e5 sweeps on either side: Monte-Carlo error ~0.005 per side
+    assert max(abs(a - b) for a, b in zip(p, p0)) < 0.03
+    if truth:
+        assert max(abs(a - b) for a, b in zip(p, truth)) < tol
+
+
+def test_legacy_cli_coal_mining_report_does_not_crash(tmp_path):
+    """`amcpt` on the reference segfaults in write_adapt_to_file: one rwm_summary_len (the last model's) is used for
+    every model's trace arrays (automix.c:266, logwrite.c:151-154).  The drop-in gives every model the longest length,
+    so the unchanged driver completes and writes all its files."""
+    r, stem, wall = _am_cli("dropin_amcpt", tmp_path, ["-n", "100000", "-N", "50000", "-s", "7"], timeout=1200)
+    print(r.stdout[-400:], r.stderr[-400:], f"amcpt on the drop-in: {wall:.1f} s")
+    assert r.returncode == 0
+    p = _report_probs(stem)
+    assert len(p) == 6 and abs(sum(p) - 1.0) < 1e-4
+    # published posterior (thesis p.177): 0.058 0.250 0.296 0.234 0.118 0.044; one chain of 5e4 sweeps
+    assert abs(p[1] - 0.25) < 0.08 and abs(p[2] - 0.30) < 0.08 and p[0] < 0.15
+    adapt = open(stem + "_adapt.data").read()
+    assert adapt.count("RWM for Model") == 6
