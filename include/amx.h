@@ -43,6 +43,10 @@ extern "C" {
 #define AMX_ENUMERIC (-6) /* non-positive-definite scatter, NaN log-posterior */
 
 /* ---- runtime ------------------------------------------------------------ */
+/* Threading: the library is driven by ONE host thread per process (one process per GPU, as the reference is a
+ * single-threaded library with global generator state).  The current stream, the deferred-sync flag, the launch
+ * counter and the drop-in layer's sampler table are process-wide and unsynchronised; only the error text is
+ * per thread.  Host callbacks are called on the calling thread. */
 const char *amx_last_error(void);
 const char *amx_version(void);
 int amx_device_count(void);
