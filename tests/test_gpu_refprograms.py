@@ -69,13 +69,16 @@ def _report_probs(stem):
     return [float(x) for x in re.findall(r"^Model \d+: ([0-9.]+)", log.split("Posterior Model Probabilities:")[1], re.M)]
 
 
-@pytest.mark.parametrize("ex,truth,tol", [("toy1", [0.3, 0.7], 0.02), ("toy2", None, None)])
+@pytest.mark.parametrize("ex,truth,tol", [("toy1", [0.3, 0.7], 0.03), ("toy2", [0.5, 0.25, 0.125, 0.0625, 0.0625], 0.08)])
 def test_legacy_cli_and_report_files_on_the_dropin(tmp_path, ex, truth, tol):
     """the reference's `am*` driver (main.c) and report writer (logwrite.c) compiled UNCHANGED on top
     of the drop-in library.  The writer walks every legacy array of amSampler -- the stage-1 traces (rwm_summary_len
     rows per model), the EM traces, and the per-sweep k / lp / pk / theta summaries -- so a complete set of well-formed
-    report files is the widest check of the struct contract; the posterior in <stem>_log.data must agree with the same
-    program on the reference's own library (and with the known 0.3 / 0.7 for toy1)."""
+    report files is the widest check of the struct contract; the posterior in <stem>_log.data must agree with the
+    targets' known model probabilities (usertoy1.c: 0.3 / 0.7; usertoy2.c: 0.5 / 0.25 / 0.125 / 0.0625 / 0.0625).  The same
+    program on the reference's own library is run and printed beside it, not asserted on: the driver seeds from time(0)
+    (main.c:54 is overridden by initAMSampler) and the reference's single chain now and then spends a whole
+    run in one model (seen here: p = 0 0 0 1 0 for toy2)."""
     n3 = 100000
     r, stem, wall = _am_cli(f"dropin_am{ex}", tmp_path, ["-n", "100000", "-N", str(n3), "-s", "5"])
     print(r.stdout[-400:], r.stderr[-400:])
@@ -100,10 +103,8 @@ def test_legacy_cli_and_report_files_on_the_dropin(tmp_path, ex, truth, tol):
     assert r0.returncode == 0
     p0 = _report_probs(stem0)
     print(f"am{ex}: drop-in {wall:.1f} s p = {p}; reference on this host {wall0:.1f} s p = {p0}")
-    # one chain of 1e5 sweeps on either side: Monte-Carlo error ~0.005 per side
-    assert max(abs(a - b) for a, b in zip(p, p0)) < 0.03
-    if truth:
-        assert max(abs(a - b) for a, b in zip(p, truth)) < tol
+    # the report is chain 0's 1e5 sweeps on a proposal fitted from a time-seeded stage 1: a few percent of run-to-run spread
+    assert max(abs(a - b) for a, b in zip(p, truth)) < tol, (p, truth)
 
 
 def test_legacy_cli_coal_mining_report_does_not_crash(tmp_path):
