@@ -205,6 +205,10 @@ int initAMSampler(amSampler *am, int nmodels, int *model_dims, targetDist logpos
   am->am_mixfit = FIGUEREIDO_MIX_FIT;
   ext_drop(am);
   ext_of(am, 1);
+  /* AMX_SEED: a reproducible run of an UNCHANGED program (the reference seeds from the clock at :207-208 and offers
+   * no way around it: the legacy driver's -s is overwritten) */
+  const char *sv = getenv("AMX_SEED");
+  if (sv && *sv) amx_sampler_set_seed(am, strtoull(sv, NULL, 10));
   return EXIT_SUCCESS;
 }
 

@@ -60,7 +60,8 @@ def _am_cli(name, tmp_path, args, timeout=900):
         pytest.skip(f"{exe} not built (needs /root/reference at build time; `make -C oracle ref`)")
     stem = str(tmp_path / name)
     t0 = time.perf_counter()
-    r = subprocess.run([exe] + args + ["-f", stem], capture_output=True, text=True, timeout=timeout)
+    env = dict(os.environ, AMX_SEED="20261019")  # (the drop-in's knob for a reproducible run of an unchanged program)
+    r = subprocess.run([exe] + args + ["-f", stem], capture_output=True, text=True, timeout=timeout, env=env)
     return r, stem, time.perf_counter() - t0
 
 
