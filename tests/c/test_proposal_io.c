@@ -80,6 +80,15 @@ int main(int argc, char **argv) {
   fprintf(f, "3\n1\n3\n2\n1.0\n2\n0.5\n0\n1\n0.4\n0\n1\n");
   fclose(f);
   CHECK(amx_sampler_load_proposal(&c, path2) != 0, "weights that do not sum to one are rejected");
+  /* weights and Cholesky diagonals feed logarithms on the device: a file that would turn into NaN there is refused here */
+  f = fopen(path2, "w");
+  fprintf(f, "3\n1\n3\n2\n1.0\n2\n1.5\n0\n1\n-0.5\n0\n1\n");
+  fclose(f);
+  CHECK(amx_sampler_load_proposal(&c, path2) != 0, "a negative weight is rejected (even when the weights sum to one)");
+  f = fopen(path2, "w");
+  fprintf(f, "3\n1\n3\n2\n1.0\n1\n1.0\n0\n0.0\n");
+  fclose(f);
+  CHECK(amx_sampler_load_proposal(&c, path2) != 0, "a zero Cholesky diagonal is rejected");
   /* Either side reads the other's files: the reference's own reader and writer (user_examples/logwrite.c,
    * compiled as it lies into oracle/_ref/libref_logwrite.so; its structs have this header's layout). */
   if (argc > 2) {
