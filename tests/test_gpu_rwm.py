@@ -2,6 +2,8 @@
 uniforms.  A stage-1 chain is ~1e4 d sweeps of a feedback loop (the scale adaptation), so the
 accept sequence is compared exactly and the continuous state with the drift bound; the first
 hundreds of sweeps are compared at the per-step bar."""
+import os
+
 import numpy as np
 import pytest
 
@@ -129,7 +131,8 @@ def test_chain_of_dimension_29_against_oracle(amx, orc, ht):
     assert _rel(r["sig_trace"][:5], o["sig_trace"][:5]) < 1e-12
 
 
-@pytest.mark.parametrize("name,k", [("toy1", 1), ("toy2", 3), ("coalmine", 2), ("coalmine", 5), ("c1_normal", 0), ("c4_mixnorm", 1)])
+@pytest.mark.parametrize("name,k", [("toy1", 1), ("toy2", 3), ("coalmine", 2), ("coalmine", 5), ("c1_normal", 0),
+                                    pytest.param("c4_mixnorm", 1, marks=pytest.mark.skipif(os.environ.get("AMX_TEST_SLOW") != "1", reason="42 s (35 s in the sequential kernel): AMX_TEST_SLOW=1; passes (profiles/r02/pytest_gpu_r02d.log)"))])
 def test_speculative_kernel_is_the_sequential_chain(amx, name, k, monkeypatch):
     """The warp-per-chain kernel (decision tree of the next five steps evaluated at once) and the
     thread-per-chain kernel run the same chain: bit-identical samples, scales and traces on Philox streams."""
